@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- particle-substeps/s of the MLS-MPM substep (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c3|c2|c5] [--impl reference]
+
+A "step" is one substep (P2G -> grid update -> G2P, the reference's advance(dt),
+cpp_validation/mls-mpm88-explained.cpp:49-180) over every particle of the workload.
+  value      whole-job particle-substeps/s with the state resident in HBM (CUDA events, max over ranks)
+  e2e        the same metric through the C-ABI with HOST buffers: mpm_upload_particles (pinned H2D) ->
+             mpm_substep(frame) -> mpm_read_particles (D2H), all inside the timed region; `frame` is
+             the reference's substeps per rendered frame (frame_dt/dt = 10, :11-12,:217)
+  roofline   dominant kernel: algorithmic bytes per launch (2D 140 B / 148 B with FLIP,
+             3D 260 B per particle-substep, attributed per kernel below) / its mean CUDA-event time
+  cpu_baseline  the oracle's restatement of advance() timed on this box's host, 1 thread (the
+             reference is single-threaded as shipped), on a bounded sample of the same scene
+`--impl reference` times that CPU path alone and prints the same line with "impl": "reference".
+Synthetic data (mpm_flip98a_b200/scenes.py); nothing here reads /root/reference.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-substeps/sec"
+FRAME = 10  # substeps per e2e call == the reference's int(frame_dt/dt), mls-mpm88-explained.cpp:217
+
+# algorithmic bytes per particle-substep, per kernel: P2G reads the full record;
+# G2P reads x,F,Jp,mat (+v with FLIP) and writes x,v,C,F,Jp
+ALGO = {2: dict(p2g=56, g2p=32 + 52, flip_extra=8), 3: dict(p2g=104, g2p=56 + 100, flip_extra=12)}
+
+WORKLOADS = {
+    # name: (description, dim, n_grid, alpha, scene builder kwargs)
+    "c2": ("2D 512^2 three-material scene, ~1M particles (BASELINE configs[1])", 2, 512, 0.0),
+    "c3": ("2D 2048^2 dam-break fluid, ~16M particles, FLIP alpha=0.95 (BASELINE configs[2])", 2, 2048, 0.95),
+    "c4": ("2D 8192^2 pool, ~245M particles, three material bands (BASELINE configs[3])", 2, 8192, 0.0),
+    "c5": ("3D 256^3 three-material collapse, ~32M particles (BASELINE configs[4])", 3, 256, 0.0),
+}
+
+
+def build_scene(name, n_grid=None):
+    from mpm_flip98a_b200 import scenes
+    _, dim, n, alpha = WORKLOADS[name]
+    n = n_grid or n
+    if name == "c2":
+        p = scenes.three_blocks_2d(n, per_side=4)
+    elif name == "c3":
+        p = scenes.dam_break_2d(n, per_side=3, width=0.47)
+    elif name == "c4":
+        p = scenes.slab_fill_2d(n, per_side=3)
+    else:
+        p = scenes.collapse_3d(n, per_side=2)
+    dt, vol = scenes.scaled_constants(n, dim)
+    return p, dim, n, alpha, dt, vol
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+        except Exception:
+            pass
+
+    def stop(self, t0, t1):
+        if self.proc:
+            self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(rows)}
+        try:
+            sm = [float(r[0]) for r in rows]
+            out["sm_mhz"] = float(np.median(sm))
+            out["sm_max_mhz"] = float(rows[0][1])
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            out["reasons"] = [n for i, n in enumerate(names) if any(r[3 + i] == "Active" for r in rows)]
+            out["power_w_max"] = max(float(r[2]) for r in rows)
+        except Exception:
+            pass
+        return out
+
+
+def cpu_sample(name, max_seconds=20.0):
+    """Times the oracle (CPU restatement of advance(), 1 thread) on a bounded sample of the workload:
+    the same scene generator at a reduced grid, warmed by a few substeps.  -> (value, description)."""
+    from oracle.cpu import Oracle, build, make_params
+    build()
+    O = Oracle()
+    _, dim, n_full, alpha = WORKLOADS[name]
+    n_small = {2: min(n_full, 1024), 3: min(n_full, 96)}[dim]
+    p, dim, n, alpha, dt, vol = build_scene(name, n_small)
+    P = make_params(dim=dim, n_grid=n, vol_p=vol, alpha=alpha)
+    O.advance(P, dt, p, 1)  # touch everything once
+    t0 = time.perf_counter()
+    steps = 0
+    while True:
+        O.advance(P, dt, p, 1)
+        steps += 1
+        el = time.perf_counter() - t0
+        if el > max_seconds or steps >= 50 or (steps >= 3 and el > max_seconds / 2):
+            break
+    val = len(p) * steps / el
+    desc = "%s scene at n_grid=%d (%d particles), %d substeps, %.1f s" % (name, n, len(p), steps, el)
+    return val, desc, (O, P, dt, p)
+
+
+def run_reference(args):
+    """Reference arm: the reference's own CPU algorithm for the path (oracle port -- the reference
+    translation unit itself only compiles for its fixed 80^2 scene), single thread as shipped."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, desc, (O, P, dt, p) = cpu_sample(args.workload, max_seconds=5.0)
+    for _ in range(args.warmup):
+        O.advance(P, dt, p, 1)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        O.advance(P, dt, p, 1)
+    el = time.perf_counter() - t0
+    value = len(p) * args.steps / el
+    descr, dim, n_grid, alpha = WORKLOADS[args.workload]
+    sample = "one substep over a bounded sample per step: %s scene at n_grid=%d, %d particles" % (
+        args.workload, P.n_grid, len(p))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "particle-substeps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": descr, "dim": dim, "n_grid": n_grid, "alpha": alpha, "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "particle-substeps/s", "cores": 1, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "particle-substeps/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "host_cores_total": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--warm-substeps", type=int, default=100, help="untimed substeps to reach a warm state")
+    ap.add_argument("--e2e-calls", type=int, default=2)
+    ap.add_argument("--naive", action="store_true", help="one-thread-per-particle kernels (MPM_FLAG_NAIVE)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import mpm_flip98a_b200 as mpm
+    from mpm_flip98a_b200.engine import FLAG_NAIVE
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
+    if world > 1:
+        raise SystemExit("multi-GPU slab path not built yet")
+
+    descr, dim, n_grid, alpha = WORKLOADS[args.workload]
+    p_np, dim, n_grid, alpha, dt, vol = build_scene(args.workload)
+    n = len(p_np)
+    words = p_np.shape[1]
+    host = torch.empty((n, words), dtype=torch.float32, pin_memory=True)  # pinned: e2e copies are async DMA
+    host.numpy()[:] = p_np
+    del p_np
+    host_out = torch.empty_like(host, pin_memory=True)
+
+    stream = torch.cuda.Stream()
+    flags = FLAG_NAIVE if args.naive else 0
+    with torch.cuda.stream(stream):
+        eng = mpm.Engine(dim=dim, n_grid=n_grid, capacity=n, dt=dt, vol_p=vol, alpha=alpha, device=local,
+                         flags=flags, stream=stream.cuda_stream)
+        eng.lib.mpm_upload_particles(eng.h, host.data_ptr(), n, 0)
+        eng.substep(args.warm_substeps)
+        eng.synchronize()
+        status = eng.poll_status()
+        if status != 0:
+            raise SystemExit("engine status %d after warm-up: %s" % (status, eng.lib.mpm_last_error(eng.h)))
+
+        # ---- value: K substeps on HBM-resident state, CUDA events on the launching stream -------
+        for _ in range(args.warmup):
+            eng.substep(1)
+        eng.synchronize()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+        eng.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_wall0 = time.time()
+        e0.record(stream)
+        for _ in range(args.steps):
+            eng.substep(1)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t_wall1 = time.time()
+        ms = e0.elapsed_time(e1)
+        prof = eng.profile()
+        eng.profile_enable(False)
+        clocks = sampler.stop(t_wall0, t_wall1)
+        if eng.poll_status() != 0:
+            raise SystemExit("engine flagged an error during the timed region")
+        value = n * args.steps / (ms * 1e-3)
+
+        # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----------------
+        eng.lib.mpm_upload_particles(eng.h, host.data_ptr(), n, 0)  # warm the path once
+        eng.substep(FRAME)
+        eng.lib.mpm_read_particles(eng.h, host_out.data_ptr(), n, 0)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_calls):
+            rc = eng.lib.mpm_upload_particles(eng.h, host.data_ptr(), n, 0)
+            assert rc == 0
+            eng.substep(FRAME)
+            rc = eng.lib.mpm_read_particles(eng.h, host_out.data_ptr(), n, 0)
+            assert rc == 0
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_value = n * FRAME * args.e2e_calls / e2e_s
+        assert torch.isfinite(host_out[:: max(1, n // 100000)]).all()
+        eng.close()
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)"
+    a = ALGO[dim]
+    algo = {"p2g": a["p2g"], "g2p": a["g2p"] + (a["flip_extra"] if alpha != 0 else 0)}
+    phases = {k: prof[k] for k in ("clear", "p2g", "grid", "g2p", "bin")}
+    dom = max(("p2g", "g2p"), key=lambda k: phases[k][0])
+    dom_ms = phases[dom][0] / max(1, prof["substeps"])
+    achieved = algo[dom] * n / (dom_ms * 1e-3) / 1e9
+    whole = (algo["p2g"] + algo["g2p"]) * value / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                "algorithmic_bytes_per_particle": algo[dom], "kernel_ms": dom_ms,
+                "whole_substep": {"algorithmic_bytes_per_particle": algo["p2g"] + algo["g2p"],
+                                  "achieved": whole, "frac": whole / peak, "frac_of_nominal_8TBs": whole / 8000.0},
+                "phase_ms_per_substep": {k: v[0] / max(1, prof["substeps"]) for k, v in phases.items()}}
+    launches = int(sum(v[1] for v in phases.values()))
+
+    line = {"metric": METRIC, "value": value, "unit": "particle-substeps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": descr, "name": args.workload, "dim": dim, "n_grid": n_grid, "particles": n,
+                       "alpha": alpha, "dt": dt, "path": "naive" if args.naive else "default",
+                       "warm_substeps": args.warm_substeps,
+                       "l2": "state (%.1f GB) larger than L2; no flush" % (n * words * 4 / 1e9)
+                       if n * words * 4 > 2.5e8 else "state fits L2 (small workload)"},
+            "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": n * words * 4,
+                    "d2h_bytes_per_step": n * words * 4, "substeps_per_step": FRAME,
+                    "call": "mpm_upload_particles + mpm_substep(%d) + mpm_read_particles, pinned host buffers" % FRAME},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+    if not args.no_cpu:
+        val, desc, _ = cpu_sample(args.workload)
+        line["cpu_baseline"] = {"value": val, "unit": "particle-substeps/s", "cores": 1, "kind": "port",
+                                "sample": desc, "host_cores_total": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

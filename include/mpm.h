@@ -1,0 +1,174 @@
+/* include/mpm.h -- C-ABI of the B200-native MLS-MPM substep engine (libmpm.so).
+ *
+ * Drop-in boundary for the `advance(dt)` path of the reference program
+ *   /root/reference/cpp_validation/mls-mpm88-explained.cpp:49-180
+ * whose state lives in two globals, `std::vector<Particle> particles` (:44) and
+ * `Vector3 grid[num_grid+1][num_grid+1]` (:47), and whose parameters are file-scope consts (:8-26).
+ * The reference has no FFI of its own; each entry point below names the reference statement(s)
+ * it replaces.  Plain C types only: pointers, sizes, PODs.  No exceptions or signals cross this
+ * boundary; every call returns 0 (MPM_OK) or a negative MPM_E_* code, and mpm_last_error() gives
+ * the text.  A handle is not thread-safe; distinct handles are independent.
+ *
+ * Particle records cross the boundary in the reference's own memory layout (:28-42):
+ *   2D, 56 bytes : x[2] v[2] F[4] C[4] Jp c      (F, C column-major like taichi.h:7575)
+ *   3D, 104 bytes: x[3] v[3] F[9] C[9] Jp c      (the 3D lift of the same struct)
+ * `c` (the reference's colour slot, :33) is the material id: an index into mpm_config.materials,
+ * any other value selects the LAST table entry (so the shipped scene's colour 0x2986CC selects the
+ * shipped constants when they are the last entry, which is the default table).
+ */
+#ifndef MPM_FLIP98A_B200_MPM_H
+#define MPM_FLIP98A_B200_MPM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPM_ABI_VERSION 1
+
+enum {
+  MPM_OK = 0,
+  MPM_E_INVALID = -1,   /* bad argument / config */
+  MPM_E_CUDA = -2,      /* CUDA runtime error (text in mpm_last_error) */
+  MPM_E_CAPACITY = -3,  /* more particles than the handle was created for */
+  MPM_E_DOMAIN = -4,    /* a particle left the grid (the reference has no bounds check, :97,:150) */
+  MPM_E_CFL = -5,       /* a particle crossed more than one bin in a substep */
+  MPM_E_STATE = -6      /* call sequence error (e.g. read before upload) */
+};
+
+enum { MPM_KIND_FLUID = 0, MPM_KIND_JELLY = 1, MPM_KIND_SNOW = 2 };
+
+/* Constitutive model of one material id.  snow == the reference's shipped path
+ * (hardening :67-69, SVD clamp :165-178); fluid / jelly follow north_star. */
+typedef struct mpm_material {
+  int kind;        /* MPM_KIND_* */
+  float E;         /* Young's modulus        (:19) */
+  float nu;        /* Poisson ratio          (:20) */
+  float hardening; /* snow: exp factor (:18); jelly: constant factor on mu/lambda; fluid: unused */
+  float sig_lo;    /* plastic clamp of singular values, reference 1-2.5e-2 (:169) */
+  float sig_hi;    /* reference 1+7.5e-3 (:169) */
+} mpm_material;
+
+enum {
+  MPM_FLAG_CAPTURE_POST_P2G = 1 << 0, /* keep a copy of the grid between P2G and the grid update */
+  MPM_FLAG_NAIVE = 1 << 1             /* one-thread-per-particle kernels with global atomics
+                                         (no binning); the small-scene / debugging path */
+};
+
+/* Everything the reference fixes at compile time (:8-26, :113, :116, :169, :175) plus the
+ * engine's own sizing.  Fill with mpm_default_config() first, then override. */
+typedef struct mpm_config {
+  int abi_version;   /* MPM_ABI_VERSION */
+  int dim;           /* 2 (reference) or 3 */
+  int n_grid;        /* cells per axis (:9 num_grid); nodes per axis = n_grid+1 */
+  float dt;          /* default substep when mpm_substep gets dt <= 0 (:11) */
+  float mass_p;      /* :17 */
+  float vol_p;       /* :18 */
+  float gravity[3];  /* :113 hard-codes (0,-200) */
+  float boundary;    /* :116 hard-codes 0.05 */
+  float jp_min;      /* :175 hard-codes 0.6 */
+  float jp_max;      /* :175 hard-codes 20 */
+  float alpha;       /* FLIP/PIC blend; 0 == the reference's pure APIC (config.py:29) */
+  int n_materials;   /* 1..4 */
+  mpm_material materials[4];
+  long long capacity; /* max particles resident on this handle */
+  int device;         /* CUDA device ordinal */
+  int flags;          /* MPM_FLAG_* */
+  /* x-slab owned by this handle: base-cell columns [slab_lo, slab_hi) of the global grid.
+   * 0 / n_grid == the whole domain (single GPU).  See the halo / migration calls below. */
+  int slab_lo, slab_hi;
+  void *stream;       /* cudaStream_t to launch on; NULL = a stream owned by the handle */
+  int bin_edge;       /* cells per bin edge for the block binning; 0 = engine default */
+  int rebin_every;    /* naive path only: re-sort the particle storage every this many substeps
+                         (0 = engine default, <0 = never); the binned path re-bins every substep */
+  int reserved[6];
+} mpm_config;
+
+typedef struct mpm_handle mpm_handle;
+
+/* Defaults = the reference as shipped (2D: n_grid 80, dt 1e-4, E 1e2, nu 0.499, hardening 1 as
+ * the LAST material; entries 0..2 = fluid / jelly / snow with the upstream mls-mpm88 constants). */
+int mpm_default_config(mpm_config *cfg, int dim);
+/* sizeof(mpm_config) as the library was compiled: lets an FFI binding check its struct layout */
+int mpm_config_bytes(void);
+
+/* replaces: the file-scope state and constants, :8-26, :44-47 */
+mpm_handle *mpm_create(const mpm_config *cfg);
+void mpm_destroy(mpm_handle *h);
+const char *mpm_last_error(const mpm_handle *h); /* h may be NULL: error of the last failed create */
+
+/* replaces: particles.push_back(...) in add_object, :191-196.  `aos` = n records of 56 B (2D) or
+ * 104 B (3D) in HOST memory (or device memory if on_device != 0).  Replaces the particle set. */
+int mpm_upload_particles(mpm_handle *h, const void *aos, long long n, int on_device);
+
+/* replaces: `for (...) advance(dt)` in main(), :214-215.  Asynchronous on the handle's stream.
+ * dt <= 0 uses cfg.dt. */
+int mpm_substep(mpm_handle *h, float dt, int n_steps);
+
+/* replaces: reading the global `particles` (:220-222).  Synchronises; records come back in the
+ * ORIGINAL upload order (the engine carries a persistent id through its sorts and migration). */
+int mpm_read_particles(mpm_handle *h, void *aos_out, long long n, int to_device);
+
+/* replaces: reading the global `grid` (:47).  stage 0 = after the grid update of the last substep
+ * ((vx,vy,1|0) per node 2D, (vx,vy,vz,1|0) 3D, exactly the reference's in-memory content);
+ * stage 1 = between P2G and the grid update ((m*vx, m*vy, m) -- needs MPM_FLAG_CAPTURE_POST_P2G).
+ * out = (slab columns) * (n_grid+1)^(dim-1) * (dim+1) floats, [i][j]([k]) row-major like :47. */
+int mpm_read_grid(mpm_handle *h, int stage, float *out);
+
+long long mpm_particle_count(const mpm_handle *h);
+int mpm_synchronize(mpm_handle *h);
+/* Sticky device-side status (MPM_E_DOMAIN / MPM_E_CFL) accumulated since the last call; synchronises. */
+int mpm_poll_status(mpm_handle *h);
+
+/* ---- per-phase device timing (CUDA events on the handle's stream) and launch counts ---------- */
+enum {
+  MPM_PHASE_CLEAR = 0, /* grid reset, :50 */
+  MPM_PHASE_P2G = 1,   /* :53-102 */
+  MPM_PHASE_GRID = 2,  /* :105-131 */
+  MPM_PHASE_G2P = 3,   /* :134-179 */
+  MPM_PHASE_BIN = 4,   /* binning / sort (no counterpart in the reference) */
+  MPM_PHASE_HALO = 5,
+  MPM_PHASE_MIGRATE = 6,
+  MPM_PHASE_COUNT = 8
+};
+typedef struct mpm_profile {
+  double ms[MPM_PHASE_COUNT];          /* device milliseconds per phase since mpm_profile_enable */
+  long long launches[MPM_PHASE_COUNT]; /* kernels launched per phase (memsets/copies not counted) */
+  long long substeps;
+} mpm_profile;
+int mpm_profile_enable(mpm_handle *h, int on); /* (re)starts accumulation from zero */
+int mpm_profile_read(mpm_handle *h, mpm_profile *out); /* synchronises */
+
+/* ---- binning: integer outputs, bit-exact against oracle_bin ------------- */
+/* Bins the CURRENT particle positions by blocks of cfg.bin_edge cells (x-major block id of the
+ * base cell, :55) with a stable sort.  Outputs (host pointers, any may be NULL):
+ *   cell[n*dim] base coordinates clamped to [0,n_grid-2], key[n] bin id, order[n] slot->upload
+ *   index, bin_start[n_bins+1].  Returns the number of bins or a negative error. */
+int mpm_bin_particles(mpm_handle *h, int *cell, int *key, int *order, int *bin_start);
+
+/* ---- x-slab multi-GPU phases (one handle per GPU; the caller moves the bytes, e.g. with
+ * ncclSend/ncclRecv or torch.distributed P2P on the device pointers returned here) ------------ */
+typedef struct mpm_halo_desc {
+  void *send_lo, *send_hi; /* device: partial sums of the 2 node columns shared with the lower / upper slab */
+  void *recv_lo, *recv_hi; /* device: where the neighbour's partial sums must land */
+  long long bytes;         /* bytes per message */
+} mpm_halo_desc;
+int mpm_halo_describe(mpm_handle *h, mpm_halo_desc *d);
+/* substep, split at its exchange points: P2G | halo sum | grid update + G2P | migration */
+int mpm_step_p2g(mpm_handle *h, float dt);
+int mpm_step_halo_add(mpm_handle *h, int have_lo, int have_hi);
+int mpm_step_grid_g2p(mpm_handle *h, float dt);
+/* emigrants of the last G2P: device buffers of (record + id) and their counts (host, after sync) */
+typedef struct mpm_migration_desc {
+  void *send_lo, *send_hi;         /* device: packed emigrant records */
+  long long n_send_lo, n_send_hi;  /* counts */
+  void *recv_lo, *recv_hi;         /* device: landing zones */
+  long long recv_capacity;         /* records per landing zone */
+  int record_bytes;                /* 56+8 (2D) or 104+8 (3D): record + 64-bit global id */
+} mpm_migration_desc;
+int mpm_migration_describe(mpm_handle *h, mpm_migration_desc *d);
+int mpm_step_immigrate(mpm_handle *h, long long n_recv_lo, long long n_recv_hi);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

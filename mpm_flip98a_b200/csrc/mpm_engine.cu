@@ -1,0 +1,606 @@
+// mpm_engine.cu -- host side of libmpm.so: the handle, its HBM arenas, the substep schedule and the
+// C-ABI of include/mpm.h.  Replaces the reference's globals and main() loop
+// (cpp_validation/mls-mpm88-explained.cpp:8-26 constants, :44-47 state, :214-215 loop).
+// There is no CPU fallback here on purpose: without a CUDA device every call fails with MPM_E_CUDA.
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mpm.h"
+#include "mpm_kernels.cuh"
+
+using namespace mpm;
+
+static thread_local std::string g_create_error;
+
+#define MPM_CUDA(call)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      char b_[512];                                                                         \
+      snprintf(b_, sizeof b_, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      this->err = b_;                                                                       \
+      return MPM_E_CUDA;                                                                    \
+    }                                                                                       \
+  } while (0)
+
+struct mpm_handle {
+  mpm_config cfg;
+  Params P;
+  int D;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  long long n = 0, cap = 0;
+  long long steps_since_sort = 0;
+  std::string err;
+
+  // particle storage: two SoA buffers (sorted reorders ping-pong between them)
+  std::vector<void *> allocs;
+  SoA<2> s2[2];
+  SoA<3> s3[2];
+  int cur = 0;
+
+  // grid
+  float4 *grid = nullptr, *grid_tap = nullptr;
+  void *vold = nullptr;
+  long long nodes = 0;
+  bool tap_valid = false;
+
+  int *status_dev = nullptr;
+  int status_host_sticky = 0;
+
+  // binning
+  BinGeom G;
+  SortBuffers sb;
+  int *bin_start = nullptr;
+  int *cell_dev = nullptr;
+  int key_bits = 0;
+
+  // AoS staging at the ABI
+  float *stage = nullptr;
+  long long stage_records = 0;
+
+  // per-phase CUDA-event timing (mpm_profile_*)
+  bool prof_on = false;
+  mpm_profile prof = {};
+  struct Span {
+    int phase;
+    cudaEvent_t a, b;
+  };
+  std::vector<Span> spans;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t get_event() {
+    cudaEvent_t e = nullptr;
+    if (!ev_pool.empty()) {
+      e = ev_pool.back();
+      ev_pool.pop_back();
+    } else {
+      cudaEventCreate(&e);
+    }
+    return e;
+  }
+  void flush_spans() {  // caller has synchronised the stream
+    for (Span &sp : spans) {
+      float ms = 0.0f;
+      if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) prof.ms[sp.phase] += ms;
+      ev_pool.push_back(sp.a);
+      ev_pool.push_back(sp.b);
+    }
+    spans.clear();
+  }
+  // RAII: times everything enqueued on the stream during its lifetime as one phase
+  struct Phase {
+    mpm_handle *h;
+    Span sp;
+    Phase(mpm_handle *h_, int phase, int launches) : h(h_) {
+      sp.phase = phase;
+      sp.a = sp.b = nullptr;
+      if (!h->prof_on) return;
+      h->prof.launches[phase] += launches;
+      sp.a = h->get_event();
+      sp.b = h->get_event();
+      cudaEventRecord(sp.a, h->stream);
+    }
+    ~Phase() {
+      if (!sp.a) return;
+      cudaEventRecord(sp.b, h->stream);
+      h->spans.push_back(sp);
+      if (h->spans.size() >= 8192) {
+        cudaStreamSynchronize(h->stream);
+        h->flush_spans();
+      }
+    }
+  };
+
+  int record_words() const { return D == 2 ? 14 : 26; }
+
+  template <typename T>
+  int dalloc(T **p, size_t count) {
+    void *q = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    MPM_CUDA(cudaMalloc(&q, bytes));
+    allocs.push_back(q);
+    *p = (T *)q;
+    return MPM_OK;
+  }
+
+  int init();
+  int upload(const void *aos, long long count, int on_device);
+  int read(void *aos_out, long long count, int to_device);
+  int rebin_storage();
+  int substep(float dt, int n_steps);
+  int step_p2g(float dt);
+  int step_grid_g2p(float dt);
+  int read_grid(int stage, float *out);
+  int bin_particles(int *cell, int *key, int *order, int *bin_start_out);
+  int poll_status();
+  template <int DD>
+  GridPtrs<DD> gp() {
+    GridPtrs<DD> g;
+    g.g = grid;
+    g.vold = vold;
+    g.nodes = nodes;
+    return g;
+  }
+  ~mpm_handle() {
+    cudaSetDevice(cfg.device);
+    for (void *p : allocs) cudaFree(p);
+    for (Span &sp : spans) {
+      cudaEventDestroy(sp.a);
+      cudaEventDestroy(sp.b);
+    }
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+  }
+};
+
+static int validate(const mpm_config &c, std::string &why) {
+  char b[256];
+#define BAD(...)                      \
+  {                                   \
+    snprintf(b, sizeof b, __VA_ARGS__); \
+    why = b;                          \
+    return MPM_E_INVALID;             \
+  }
+  if (c.abi_version != MPM_ABI_VERSION) BAD("abi_version %d != %d", c.abi_version, MPM_ABI_VERSION);
+  if (c.dim != 2 && c.dim != 3) BAD("dim must be 2 or 3 (got %d)", c.dim);
+  if (c.n_grid < 4) BAD("n_grid must be >= 4 (got %d)", c.n_grid);
+  if (c.dim == 2 && c.n_grid > 32766) BAD("n_grid too large for 2D (%d)", c.n_grid);
+  if (c.dim == 3 && c.n_grid > 2046) BAD("n_grid too large for 3D (%d)", c.n_grid);
+  if (c.n_materials < 1 || c.n_materials > 4) BAD("n_materials must be 1..4 (got %d)", c.n_materials);
+  for (int m = 0; m < c.n_materials; m++)
+    if (c.materials[m].kind < 0 || c.materials[m].kind > 2) BAD("material %d: unknown kind %d", m, c.materials[m].kind);
+  if (c.capacity < 1 || c.capacity > 2000000000LL) BAD("capacity must be in [1, 2e9] (got %lld)", c.capacity);
+  if (c.slab_lo < 0 || c.slab_hi > c.n_grid || c.slab_lo >= c.slab_hi) BAD("bad slab [%d,%d)", c.slab_lo, c.slab_hi);
+  if (c.bin_edge < 0 || c.bin_edge > 64) BAD("bin_edge must be 0..64 (got %d)", c.bin_edge);
+  return MPM_OK;
+#undef BAD
+}
+
+int mpm_handle::init() {
+  D = cfg.dim;
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  if (cfg.stream) {
+    stream = (cudaStream_t)cfg.stream;
+  } else {
+    MPM_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    own_stream = true;
+  }
+  // kernel-side constants, computed in fp32 in the reference's expression order (:12-13, :25-26)
+  memset(&P, 0, sizeof P);
+  P.n_grid = cfg.n_grid;
+  P.n1 = cfg.n_grid + 1;
+  P.dx = 1.0f / cfg.n_grid;
+  P.inv_dx = 1.0f / P.dx;
+  P.mass_p = cfg.mass_p;
+  P.vol_p = cfg.vol_p;
+  for (int k = 0; k < 3; k++) P.gravity[k] = cfg.gravity[k];
+  P.boundary = cfg.boundary;
+  P.jp_min = cfg.jp_min;
+  P.jp_max = cfg.jp_max;
+  P.alpha = cfg.alpha;
+  P.n_materials = cfg.n_materials;
+  for (int m = 0; m < cfg.n_materials; m++) {
+    const mpm_material &s = cfg.materials[m];
+    Material &d = P.mat[m];
+    d.kind = s.kind;
+    volatile float E = s.E, nu = s.nu;  // volatile: keep the divisions in fp32, unfused, as written
+    d.mu_0 = E / (2 * (1 + nu));
+    d.lambda_0 = E * nu / ((1 + nu) * (1 - 2 * nu));
+    d.hardening = s.hardening;
+    d.sig_lo = s.sig_lo;
+    d.sig_hi = s.sig_hi;
+  }
+  P.slab_lo = cfg.slab_lo;
+  P.slab_hi = cfg.slab_hi;
+  int xhi = cfg.slab_hi < cfg.n_grid - 1 ? cfg.slab_hi : cfg.n_grid - 1;  // one past the last owned base column
+  P.ncol = xhi - cfg.slab_lo + 2;
+  cap = cfg.capacity;
+
+  nodes = (long long)P.ncol * P.n1 * (D == 3 ? P.n1 : 1);
+  int rc;
+  if ((rc = dalloc(&grid, (size_t)nodes))) return rc;
+  if (cfg.alpha != 0.0f) {
+    char *v;
+    if ((rc = dalloc(&v, (size_t)nodes * (D == 2 ? 8 : 16)))) return rc;
+    vold = v;
+  }
+  if (cfg.flags & MPM_FLAG_CAPTURE_POST_P2G)
+    if ((rc = dalloc(&grid_tap, (size_t)nodes))) return rc;
+  if ((rc = dalloc(&status_dev, 4))) return rc;
+  MPM_CUDA(cudaMemsetAsync(status_dev, 0, 16, stream));
+
+  for (int b = 0; b < 2; b++) {
+    if (D == 2) {
+      SoA<2> &s = s2[b];
+      if ((rc = dalloc(&s.x, cap)) || (rc = dalloc(&s.v, cap)) || (rc = dalloc(&s.C, cap)) || (rc = dalloc(&s.F, cap)) ||
+          (rc = dalloc(&s.Jp, cap)) || (rc = dalloc(&s.mat, cap)) || (rc = dalloc(&s.id, cap)))
+        return rc;
+    } else {
+      SoA<3> &s = s3[b];
+      if ((rc = dalloc(&s.xj, cap)) || (rc = dalloc(&s.vm, cap)) || (rc = dalloc(&s.id, cap))) return rc;
+      for (int k = 0; k < 9; k++)
+        if ((rc = dalloc(&s.C[k], cap)) || (rc = dalloc(&s.F[k], cap))) return rc;
+    }
+  }
+
+  int edge = cfg.bin_edge > 0 ? cfg.bin_edge : (D == 2 ? 8 : 4);
+  G = make_bin_geom(P, D, edge);
+  key_bits = 1;
+  while ((1LL << key_bits) < G.n_bins) key_bits++;
+  sb.capacity = cap;
+  for (int b = 0; b < 2; b++)
+    if ((rc = dalloc(&sb.key[b], cap)) || (rc = dalloc(&sb.val[b], cap))) return rc;
+  if ((rc = dalloc(&sb.hist, sort_hist_elems(cap)))) return rc;
+  if ((rc = dalloc(&sb.scan_tmp, scan_tmp_elems((long long)sort_hist_elems(cap))))) return rc;
+  if ((rc = dalloc(&bin_start, (size_t)G.n_bins + 1))) return rc;
+
+  stage_records = cap < (1LL << 22) ? cap : (1LL << 22);  // <= 4M records (224 / 416 MB) per chunk
+  if ((rc = dalloc(&stage, (size_t)stage_records * record_words()))) return rc;
+  MPM_CUDA(cudaStreamSynchronize(stream));
+  return MPM_OK;
+}
+
+int mpm_handle::upload(const void *aos, long long count, int on_device) {
+  if (count < 0 || (count > 0 && !aos)) {
+    err = "upload: bad arguments";
+    return MPM_E_INVALID;
+  }
+  if (count > cap) {
+    err = "upload: more particles than capacity";
+    return MPM_E_CAPACITY;
+  }
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  const int W = record_words();
+  for (long long first = 0; first < count; first += stage_records) {
+    long long c = count - first < stage_records ? count - first : stage_records;
+    const float *src = (const float *)aos + first * W;
+    const float *dev_src = src;
+    if (!on_device) {
+      MPM_CUDA(cudaMemcpyAsync(stage, src, (size_t)c * W * 4, cudaMemcpyHostToDevice, stream));
+      dev_src = stage;
+    }
+    if (D == 2) launch_aos_to_soa<2>(dev_src, first, c, s2[cur], stream);
+    else launch_aos_to_soa<3>(dev_src, first, c, s3[cur], stream);
+    // the staging buffer is reused by the next chunk; the copy and the kernel are stream-ordered
+  }
+  MPM_CUDA(cudaGetLastError());
+  n = count;
+  tap_valid = false;
+  int rc = rebin_storage();
+  if (rc) return rc;
+  MPM_CUDA(cudaStreamSynchronize(stream));  // the caller may free `aos` on return
+  return MPM_OK;
+}
+
+// keys -> stable sort -> physical reorder into the other SoA buffer; bin_start refreshed
+int mpm_handle::rebin_storage() {
+  steps_since_sort = 0;
+  if (n == 0) return MPM_OK;
+  Phase ph(this, MPM_PHASE_BIN, 4 + 3 * ((key_bits + 7) / 8));
+  if (D == 2) launch_bin_keys<2>(P, G, s2[cur], n, nullptr, sb.key[0], status_dev, false, stream);
+  else launch_bin_keys<3>(P, G, s3[cur], n, nullptr, sb.key[0], status_dev, false, stream);
+  launch_iota(sb.val[0], n, stream);
+  int r = radix_sort_pairs(sb, n, key_bits, stream);
+  launch_bin_starts(sb.key[r], n, G.n_bins, bin_start, stream);
+  if (D == 2) launch_reorder<2>(s2[cur], s2[cur ^ 1], sb.val[r], n, stream);
+  else launch_reorder<3>(s3[cur], s3[cur ^ 1], sb.val[r], n, stream);
+  cur ^= 1;
+  MPM_CUDA(cudaGetLastError());
+  return MPM_OK;
+}
+
+int mpm_handle::read(void *aos_out, long long count, int to_device) {
+  if (count < 0 || count > n || (count > 0 && !aos_out)) {
+    err = "read: bad arguments";
+    return MPM_E_INVALID;
+  }
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  const int W = record_words();
+  for (long long first = 0; first < count; first += stage_records) {
+    long long c = count - first < stage_records ? count - first : stage_records;
+    float *dst = (float *)aos_out + first * W;
+    float *dev_dst = to_device ? dst : stage;
+    if (D == 2) launch_soa_to_aos<2>(s2[cur], n, first, c, dev_dst, stream);
+    else launch_soa_to_aos<3>(s3[cur], n, first, c, dev_dst, stream);
+    if (!to_device) MPM_CUDA(cudaMemcpyAsync(dst, stage, (size_t)c * W * 4, cudaMemcpyDeviceToHost, stream));
+  }
+  MPM_CUDA(cudaGetLastError());
+  MPM_CUDA(cudaStreamSynchronize(stream));
+  return MPM_OK;
+}
+
+int mpm_handle::step_p2g(float dt) {
+  {
+    Phase ph(this, MPM_PHASE_CLEAR, 0);
+    MPM_CUDA(cudaMemsetAsync(grid, 0, (size_t)nodes * sizeof(float4), stream));  // :50
+  }
+  Phase ph(this, MPM_PHASE_P2G, n > 0 ? 1 : 0);
+  if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], n, gp<2>(), status_dev, stream);
+  else launch_p2g_naive<3>(P, dt, s3[cur], n, gp<3>(), status_dev, stream);
+  return MPM_OK;
+}
+
+int mpm_handle::step_grid_g2p(float dt) {
+  if (grid_tap) {
+    MPM_CUDA(cudaMemcpyAsync(grid_tap, grid, (size_t)nodes * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+    tap_valid = true;
+  }
+  {
+    Phase ph(this, MPM_PHASE_GRID, 1);
+    if (D == 2) launch_grid_update<2>(P, dt, gp<2>(), stream);
+    else launch_grid_update<3>(P, dt, gp<3>(), stream);
+  }
+  {
+    Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
+    if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], n, gp<2>(), stream);
+    else launch_g2p_naive<3>(P, dt, s3[cur], n, gp<3>(), stream);
+  }
+  if (prof_on) prof.substeps++;
+  return MPM_OK;
+}
+
+int mpm_handle::substep(float dt, int n_steps) {
+  if (n_steps < 0) {
+    err = "substep: n_steps < 0";
+    return MPM_E_INVALID;
+  }
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  if (!(dt > 0)) dt = cfg.dt;
+  int every = cfg.rebin_every == 0 ? 32 : cfg.rebin_every;
+  for (int s = 0; s < n_steps; s++) {
+    int rc;
+    if (every > 0 && steps_since_sort >= every)
+      if ((rc = rebin_storage())) return rc;
+    if ((rc = step_p2g(dt))) return rc;
+    if ((rc = step_grid_g2p(dt))) return rc;
+    steps_since_sort++;
+  }
+  MPM_CUDA(cudaGetLastError());
+  return MPM_OK;
+}
+
+int mpm_handle::read_grid(int stage_id, float *out) {
+  if (!out || (stage_id != 0 && stage_id != 1)) {
+    err = "read_grid: bad arguments";
+    return MPM_E_INVALID;
+  }
+  if (stage_id == 1 && (!grid_tap || !tap_valid)) {
+    err = "read_grid: stage 1 needs MPM_FLAG_CAPTURE_POST_P2G and at least one substep";
+    return MPM_E_STATE;
+  }
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  std::vector<float4> host((size_t)nodes);
+  MPM_CUDA(cudaMemcpyAsync(host.data(), stage_id == 1 ? grid_tap : grid, (size_t)nodes * sizeof(float4),
+                           cudaMemcpyDeviceToHost, stream));
+  MPM_CUDA(cudaStreamSynchronize(stream));
+  for (long long i = 0; i < nodes; i++) {
+    const float4 &g = host[(size_t)i];
+    if (D == 2) {
+      out[3 * i + 0] = g.x;
+      out[3 * i + 1] = g.y;
+      out[3 * i + 2] = g.z;
+    } else {
+      out[4 * i + 0] = g.x;
+      out[4 * i + 1] = g.y;
+      out[4 * i + 2] = g.z;
+      out[4 * i + 3] = g.w;
+    }
+  }
+  return MPM_OK;
+}
+
+int mpm_handle::bin_particles(int *cell, int *key, int *order, int *bin_start_out) {
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  if (n == 0) return G.n_bins;
+  int rc;
+  if (cell && !cell_dev)
+    if ((rc = dalloc(&cell_dev, (size_t)cap * D))) return rc;
+  // keys in UPLOAD order (scatter by id) so that the stable sort reproduces oracle_bin's permutation
+  if (D == 2) launch_bin_keys<2>(P, G, s2[cur], n, cell ? cell_dev : nullptr, sb.key[0], status_dev, true, stream);
+  else launch_bin_keys<3>(P, G, s3[cur], n, cell ? cell_dev : nullptr, sb.key[0], status_dev, true, stream);
+  if (key) MPM_CUDA(cudaMemcpyAsync(key, sb.key[0], (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+  if (cell) MPM_CUDA(cudaMemcpyAsync(cell, cell_dev, (size_t)n * D * 4, cudaMemcpyDeviceToHost, stream));
+  launch_iota(sb.val[0], n, stream);
+  int r = radix_sort_pairs(sb, n, key_bits, stream);
+  // bin starts into the histogram scratch (bin_start itself belongs to the storage order)
+  int *tmp_start = (int *)sb.hist;
+  if ((size_t)G.n_bins + 1 > sort_hist_elems(cap)) {
+    err = "bin_particles: scratch too small";
+    return MPM_E_INVALID;
+  }
+  if (order) MPM_CUDA(cudaMemcpyAsync(order, sb.val[r], (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
+  launch_bin_starts(sb.key[r], n, G.n_bins, tmp_start, stream);
+  if (bin_start_out)
+    MPM_CUDA(cudaMemcpyAsync(bin_start_out, tmp_start, ((size_t)G.n_bins + 1) * 4, cudaMemcpyDeviceToHost, stream));
+  MPM_CUDA(cudaGetLastError());
+  MPM_CUDA(cudaStreamSynchronize(stream));
+  return G.n_bins;
+}
+
+int mpm_handle::poll_status() {
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  int st = 0;
+  MPM_CUDA(cudaMemcpyAsync(&st, status_dev, 4, cudaMemcpyDeviceToHost, stream));
+  MPM_CUDA(cudaMemsetAsync(status_dev, 0, 4, stream));
+  MPM_CUDA(cudaStreamSynchronize(stream));
+  if (st & STATUS_DOMAIN) {
+    err = "a particle left the grid (base cell clamped)";
+    return MPM_E_DOMAIN;
+  }
+  if (st & STATUS_CFL) {
+    err = "a particle crossed more than one bin in one substep";
+    return MPM_E_CFL;
+  }
+  return MPM_OK;
+}
+
+// ================================================================================================
+// C-ABI
+// ================================================================================================
+extern "C" {
+
+int mpm_default_config(mpm_config *c, int dim) {
+  if (!c || (dim != 2 && dim != 3)) return MPM_E_INVALID;
+  memset(c, 0, sizeof *c);
+  c->abi_version = MPM_ABI_VERSION;
+  c->dim = dim;
+  c->n_grid = 80;      // :9
+  c->dt = 1e-4f;       // :11
+  c->mass_p = 1.0f;    // :17
+  c->vol_p = 1.0f;     // :18
+  c->gravity[0] = 0.0f;
+  c->gravity[1] = -200.0f;  // :113
+  c->gravity[2] = 0.0f;
+  c->boundary = 0.05f;  // :116
+  c->jp_min = 0.6f;     // :175
+  c->jp_max = 20.0f;
+  c->alpha = 0.0f;
+  c->n_materials = 4;
+  const float lo = 1.0f - 2.5e-2f, hi = 1.0f + 7.5e-3f;  // :169
+  mpm_material fluid = {MPM_KIND_FLUID, 1e4f, 0.2f, 0.0f, lo, hi};
+  mpm_material jelly = {MPM_KIND_JELLY, 1e4f, 0.2f, 0.3f, lo, hi};
+  mpm_material snow = {MPM_KIND_SNOW, 1e4f, 0.2f, 10.0f, lo, hi};
+  mpm_material shipped = {MPM_KIND_SNOW, 1e2f, 0.499f, 1.0f, lo, hi};  // :18-20
+  c->materials[0] = fluid;
+  c->materials[1] = jelly;
+  c->materials[2] = snow;
+  c->materials[3] = shipped;
+  c->capacity = 1 << 20;
+  c->device = 0;
+  c->flags = 0;
+  c->slab_lo = 0;
+  c->slab_hi = c->n_grid;
+  return MPM_OK;
+}
+
+int mpm_config_bytes(void) { return (int)sizeof(mpm_config); }
+
+mpm_handle *mpm_create(const mpm_config *cfg) {
+  if (!cfg) {
+    g_create_error = "mpm_create: NULL config";
+    return nullptr;
+  }
+  std::string why;
+  if (validate(*cfg, why) != MPM_OK) {
+    g_create_error = "mpm_create: " + why;
+    return nullptr;
+  }
+  mpm_handle *h = new (std::nothrow) mpm_handle();
+  if (!h) {
+    g_create_error = "mpm_create: out of host memory";
+    return nullptr;
+  }
+  h->cfg = *cfg;
+  int rc = h->init();
+  if (rc != MPM_OK) {
+    g_create_error = "mpm_create: " + h->err;
+    delete h;
+    return nullptr;
+  }
+  return h;
+}
+
+void mpm_destroy(mpm_handle *h) { delete h; }
+
+const char *mpm_last_error(const mpm_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int mpm_upload_particles(mpm_handle *h, const void *aos, long long n, int on_device) {
+  return h ? h->upload(aos, n, on_device) : MPM_E_INVALID;
+}
+int mpm_substep(mpm_handle *h, float dt, int n_steps) { return h ? h->substep(dt, n_steps) : MPM_E_INVALID; }
+int mpm_read_particles(mpm_handle *h, void *aos_out, long long n, int to_device) {
+  return h ? h->read(aos_out, n, to_device) : MPM_E_INVALID;
+}
+int mpm_read_grid(mpm_handle *h, int stage, float *out) { return h ? h->read_grid(stage, out) : MPM_E_INVALID; }
+long long mpm_particle_count(const mpm_handle *h) { return h ? h->n : -1; }
+int mpm_synchronize(mpm_handle *h) {
+  if (!h) return MPM_E_INVALID;
+  cudaSetDevice(h->cfg.device);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) {
+    h->err = std::string("synchronize: ") + cudaGetErrorString(e);
+    return MPM_E_CUDA;
+  }
+  return MPM_OK;
+}
+int mpm_poll_status(mpm_handle *h) { return h ? h->poll_status() : MPM_E_INVALID; }
+int mpm_profile_enable(mpm_handle *h, int on) {
+  if (!h) return MPM_E_INVALID;
+  cudaSetDevice(h->cfg.device);
+  cudaStreamSynchronize(h->stream);
+  h->flush_spans();
+  memset(&h->prof, 0, sizeof h->prof);
+  h->prof_on = on != 0;
+  return MPM_OK;
+}
+int mpm_profile_read(mpm_handle *h, mpm_profile *out) {
+  if (!h || !out) return MPM_E_INVALID;
+  cudaSetDevice(h->cfg.device);
+  cudaError_t e = cudaStreamSynchronize(h->stream);
+  if (e != cudaSuccess) {
+    h->err = std::string("profile_read: ") + cudaGetErrorString(e);
+    return MPM_E_CUDA;
+  }
+  h->flush_spans();
+  *out = h->prof;
+  return MPM_OK;
+}
+int mpm_bin_particles(mpm_handle *h, int *cell, int *key, int *order, int *bin_start) {
+  return h ? h->bin_particles(cell, key, order, bin_start) : MPM_E_INVALID;
+}
+
+// ---- x-slab phases -------------------------------------------------------------------------------
+int mpm_halo_describe(mpm_handle *h, mpm_halo_desc *d) {
+  if (!h || !d) return MPM_E_INVALID;
+  h->err = "halo exchange: not built yet";
+  return MPM_E_STATE;
+}
+int mpm_step_p2g(mpm_handle *h, float dt) {
+  if (!h) return MPM_E_INVALID;
+  if (!(dt > 0)) dt = h->cfg.dt;
+  return h->step_p2g(dt);
+}
+int mpm_step_halo_add(mpm_handle *h, int, int) {
+  if (!h) return MPM_E_INVALID;
+  h->err = "halo exchange: not built yet";
+  return MPM_E_STATE;
+}
+int mpm_step_grid_g2p(mpm_handle *h, float dt) {
+  if (!h) return MPM_E_INVALID;
+  if (!(dt > 0)) dt = h->cfg.dt;
+  return h->step_grid_g2p(dt);
+}
+int mpm_migration_describe(mpm_handle *h, mpm_migration_desc *d) {
+  if (!h || !d) return MPM_E_INVALID;
+  h->err = "migration: not built yet";
+  return MPM_E_STATE;
+}
+int mpm_step_immigrate(mpm_handle *h, long long, long long) {
+  if (!h) return MPM_E_INVALID;
+  h->err = "migration: not built yet";
+  return MPM_E_STATE;
+}
+}

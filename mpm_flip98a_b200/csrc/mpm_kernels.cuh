@@ -1,0 +1,63 @@
+// mpm_kernels.cuh -- host-callable launchers of the substep kernels (defined in mpm_kernels.cu,
+// mpm_sort.cu).  Internal to libmpm.so; the public boundary is include/mpm.h.
+#pragma once
+#include "mpm_common.cuh"
+
+namespace mpm {
+
+template <int D>
+struct GridPtrs {
+  float4 *g;     // node array (see mpm_common.cuh)
+  void *vold;    // pre-gravity node velocity: float2 (2D) / float4 (3D); NULL when alpha == 0
+  long long nodes;
+};
+
+// ---- naive path: one thread per particle, vector REDs straight into L2 -------------------------
+template <int D>
+void launch_p2g_naive(const Params &P, float dt, const SoA<D> &s, long long n, GridPtrs<D> g, int *status,
+                      cudaStream_t st);
+template <int D>
+void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long n, GridPtrs<D> g, cudaStream_t st);
+template <int D>
+void launch_grid_update(const Params &P, float dt, GridPtrs<D> g, cudaStream_t st);
+
+// ---- AoS <-> SoA at the C-ABI ------------------------------------------------------------------
+// records [first, first+count) of the caller's AoS -> SoA slots [first, first+count), id = index
+template <int D>
+void launch_aos_to_soa(const float *aos, long long first, long long count, const SoA<D> &s, cudaStream_t st);
+// every particle whose id lies in [id0, id0+count) writes its record to aos[(id - id0)]
+template <int D>
+void launch_soa_to_aos(const SoA<D> &s, long long n, long long id0, long long count, float *aos, cudaStream_t st);
+// dst[slot] = src[order[slot]] for all fields
+template <int D>
+void launch_reorder(const SoA<D> &src, const SoA<D> &dst, const int *order, long long n, cudaStream_t st);
+
+// ---- binning -----------------------------------------------------------------------------------
+struct BinGeom {
+  int edge;      // cells per bin edge
+  int nb[3];     // bins per axis (x: over the owned slab)
+  int n_bins;
+};
+BinGeom make_bin_geom(const Params &P, int dim, int edge);
+// cell[n*D] (may be NULL), key[n]; flags STATUS_DOMAIN
+template <int D>
+void launch_bin_keys(const Params &P, const BinGeom &G, const SoA<D> &s, long long n, int *cell, unsigned *key,
+                     int *status, bool by_id, cudaStream_t st);
+// stable LSD radix sort of (key, val) pairs on `bits` key bits; returns which buffer holds the result
+struct SortBuffers {
+  unsigned *key[2];
+  int *val[2];
+  unsigned *hist;       // 256 * n_tiles
+  unsigned *scan_tmp;   // scratch for the scan
+  long long capacity;
+};
+size_t sort_hist_elems(long long n);
+size_t scan_tmp_elems(long long n);
+int radix_sort_pairs(SortBuffers &B, long long n, int bits, cudaStream_t st);
+// bin_start[n_bins+1] from sorted keys
+void launch_bin_starts(const unsigned *sorted_key, long long n, int n_bins, int *bin_start, cudaStream_t st);
+void launch_iota(int *v, long long n, cudaStream_t st);
+// exclusive scan of unsigned data[n] in place (tmp: scan_tmp_elems(n))
+void exclusive_scan_u32(unsigned *data, long long n, unsigned *tmp, cudaStream_t st);
+
+}  // namespace mpm

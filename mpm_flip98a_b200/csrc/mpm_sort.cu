@@ -1,0 +1,240 @@
+// mpm_sort.cu -- binning of particles by grid block: keys, a stable LSD radix sort, bin starts.
+//
+// The bin key is the x-major linear id of the block of `bin_edge` cells that contains the particle's
+// BASE cell, base = trunc(x*inv_dx - 0.5) (cpp_validation/mls-mpm88-explained.cpp:55; truncation,
+// taichi.h:7185-7187), clamped into the grid.  All outputs are integers and are bit-exact against
+// the CPU binning oracle (oracle_bin in oracle/mpm_oracle.cpp): same cells, same keys, and -- the
+// sort being stable -- the same permutation.
+#include "mpm_kernels.cuh"
+
+namespace mpm {
+
+BinGeom make_bin_geom(const Params &P, int dim, int edge) {
+  BinGeom G;
+  G.edge = edge;
+  // bases run over [0, n_grid-2] globally; x over the owned slab [slab_lo, min(slab_hi, n_grid-1))
+  int xhi = P.slab_hi < P.n_grid - 1 ? P.slab_hi : P.n_grid - 1;
+  G.nb[0] = (xhi - P.slab_lo + edge - 1) / edge;
+  G.nb[1] = (P.n_grid - 1 + edge - 1) / edge;
+  G.nb[2] = dim == 3 ? G.nb[1] : 1;
+  G.n_bins = G.nb[0] * G.nb[1] * G.nb[2];
+  return G;
+}
+
+template <int D>
+__global__ void k_bin_keys(Params P, BinGeom G, SoA<D> s, long long n, int *__restrict__ cell,
+                           unsigned *__restrict__ key, int *__restrict__ status, bool by_id) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float x[D];
+  load_pos(s, i, x);
+  int base[D];
+#pragma unroll
+  for (int k = 0; k < D; k++) base[k] = base_coord(x[k], P.inv_dx);
+  int bad = clamp_base<D>(P, base);
+  if (bad) atomicOr(status, bad);
+  unsigned kk = (unsigned)((base[0] - P.slab_lo) / G.edge);
+#pragma unroll
+  for (int k = 1; k < D; k++) kk = kk * (unsigned)G.nb[k] + (unsigned)(base[k] / G.edge);
+  const long long o = by_id ? (long long)s.id[i] : i;  // by_id: outputs indexed by upload order
+  key[o] = kk;
+  if (cell) {
+#pragma unroll
+    for (int k = 0; k < D; k++) cell[o * D + k] = base[k];
+  }
+}
+template <int D>
+void launch_bin_keys(const Params &P, const BinGeom &G, const SoA<D> &s, long long n, int *cell, unsigned *key,
+                     int *status, bool by_id, cudaStream_t st) {
+  if (n <= 0) return;
+  k_bin_keys<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, G, s, n, cell, key, status, by_id);
+}
+template void launch_bin_keys<2>(const Params &, const BinGeom &, const SoA<2> &, long long, int *, unsigned *, int *,
+                                 bool, cudaStream_t);
+template void launch_bin_keys<3>(const Params &, const BinGeom &, const SoA<3> &, long long, int *, unsigned *, int *,
+                                 bool, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan (u32), three-phase, recursive on the block sums.  1024 elements per block.
+// ------------------------------------------------------------------------------------------------
+static const int SCAN_BLOCK = 1024;  // elements per CTA (256 threads x 4)
+
+__device__ __forceinline__ unsigned warp_incl_scan(unsigned v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// scans one block of 1024 in place; writes the block total to sums[blockIdx] (if sums)
+__global__ void __launch_bounds__(256) k_scan_block(unsigned *__restrict__ data, long long n, unsigned *__restrict__ sums) {
+  __shared__ unsigned wsum[8];
+  long long base = (long long)blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+  unsigned v[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] = base + k < n ? data[base + k] : 0u;
+  unsigned tsum = v[0] + v[1] + v[2] + v[3];
+  unsigned inc = warp_incl_scan(tsum);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    unsigned s = lane < 8 ? wsum[lane] : 0u;
+    unsigned si = warp_incl_scan(s);
+    if (lane < 8) wsum[lane] = si - s;
+    if (lane == 7 && sums) sums[blockIdx.x] = si;
+  }
+  __syncthreads();
+  unsigned run = wsum[w] + inc - tsum;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (base + k < n) data[base + k] = run;
+    run += v[k];
+  }
+}
+__global__ void __launch_bounds__(256) k_scan_add(unsigned *__restrict__ data, long long n, const unsigned *__restrict__ sums) {
+  long long base = (long long)blockIdx.x * SCAN_BLOCK + threadIdx.x * 4;
+  unsigned add = sums[blockIdx.x];
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (base + k < n) data[base + k] += add;
+}
+size_t scan_tmp_elems(long long n) {
+  size_t total = 0;
+  while (n > 1) {
+    n = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+    total += (size_t)n + 1;
+    if (n == 1) break;
+  }
+  return total + 4;
+}
+void exclusive_scan_u32(unsigned *data, long long n, unsigned *tmp, cudaStream_t st) {
+  if (n <= 0) return;
+  long long blocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  if (blocks == 1) {
+    k_scan_block<<<1, 256, 0, st>>>(data, n, nullptr);
+    return;
+  }
+  k_scan_block<<<(unsigned)blocks, 256, 0, st>>>(data, n, tmp);
+  exclusive_scan_u32(tmp, blocks, tmp + blocks + 1, st);
+  k_scan_add<<<(unsigned)blocks, 256, 0, st>>>(data, n, tmp);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSD radix sort, 8 bits per pass, stable.  Tile = 256 threads x 16 keys, warp w owns the
+// contiguous segment [w*512, (w+1)*512) of its tile and walks it in rounds of 32 so that
+// "earlier in memory" == "earlier (round, lane)" -- which is what makes the in-tile rank stable.
+// ------------------------------------------------------------------------------------------------
+static const int RS_THREADS = 256, RS_ITEMS = 16, RS_TILE = RS_THREADS * RS_ITEMS, RS_WARPS = RS_THREADS / 32;
+
+size_t sort_hist_elems(long long n) { return (size_t)256 * (size_t)((n + RS_TILE - 1) / RS_TILE) + 1; }
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_hist(const unsigned *__restrict__ key, long long n, int shift,
+                                                        unsigned *__restrict__ hist, unsigned n_tiles) {
+  __shared__ unsigned cnt[256];
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  long long base = (long long)blockIdx.x * RS_TILE;
+#pragma unroll 4
+  for (int r = 0; r < RS_ITEMS; r++) {
+    long long i = base + r * RS_THREADS + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[(key[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * n_tiles + blockIdx.x] = cnt[threadIdx.x];  // digit-major for the scan
+}
+
+__global__ void __launch_bounds__(RS_THREADS) k_rs_scatter(const unsigned *__restrict__ key_in, const int *__restrict__ val_in,
+                                                           unsigned *__restrict__ key_out, int *__restrict__ val_out,
+                                                           long long n, int shift, const unsigned *__restrict__ hist,
+                                                           unsigned n_tiles) {
+  __shared__ unsigned cnt[RS_WARPS][256];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < RS_WARPS * 256; k += RS_THREADS) (&cnt[0][0])[k] = 0;
+  __syncthreads();
+  const long long seg = (long long)blockIdx.x * RS_TILE + (long long)w * (32 * RS_ITEMS);
+  unsigned kreg[RS_ITEMS];
+  unsigned rank[RS_ITEMS];
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    long long i = seg + r * 32 + lane;
+    bool valid = i < n;
+    unsigned k = valid ? key_in[i] : 0xffffffffu;
+    kreg[r] = k;
+    unsigned d = (k >> shift) & 255u;
+    // invalid lanes get a digit of their own (256) so they never join a valid group
+    unsigned m = __match_any_sync(0xffffffffu, valid ? d : 256u);
+    int leader = __ffs(m) - 1;
+    unsigned before = __popc(m & ((1u << lane) - 1u));
+    unsigned old = 0;
+    if (valid && lane == leader) {
+      old = cnt[w][d];
+      cnt[w][d] = old + __popc(m);
+    }
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + before;
+    __syncwarp();
+  }
+  __syncthreads();
+  {  // exclusive prefix over the warps, per digit, plus the tile's global base
+    unsigned d = threadIdx.x;
+    unsigned run = hist[(size_t)d * n_tiles + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < RS_WARPS; ww++) {
+      unsigned c = cnt[ww][d];
+      cnt[ww][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < RS_ITEMS; r++) {
+    long long i = seg + r * 32 + lane;
+    if (i < n) {
+      unsigned d = (kreg[r] >> shift) & 255u;
+      unsigned pos = cnt[w][d] + rank[r];
+      key_out[pos] = kreg[r];
+      val_out[pos] = val_in[i];
+    }
+  }
+}
+
+int radix_sort_pairs(SortBuffers &B, long long n, int bits, cudaStream_t st) {
+  int cur = 0;
+  if (n <= 0) return cur;
+  unsigned n_tiles = (unsigned)((n + RS_TILE - 1) / RS_TILE);
+  for (int shift = 0; shift < bits; shift += 8) {
+    k_rs_hist<<<n_tiles, RS_THREADS, 0, st>>>(B.key[cur], n, shift, B.hist, n_tiles);
+    exclusive_scan_u32(B.hist, (long long)256 * n_tiles, B.scan_tmp, st);
+    k_rs_scatter<<<n_tiles, RS_THREADS, 0, st>>>(B.key[cur], B.val[cur], B.key[cur ^ 1], B.val[cur ^ 1], n, shift,
+                                                 B.hist, n_tiles);
+    cur ^= 1;
+  }
+  return cur;
+}
+
+// bin_start[b] = first slot whose key >= b  (bin_start[n_bins] = n)
+__global__ void k_bin_starts(const unsigned *__restrict__ key, long long n, int n_bins, int *__restrict__ bin_start) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  long long prev = i == 0 ? -1 : (long long)key[i - 1];
+  long long cur = i == n ? (long long)n_bins : (long long)key[i];
+  for (long long b = prev + 1; b <= cur; b++) bin_start[b] = (int)i;
+}
+void launch_bin_starts(const unsigned *sorted_key, long long n, int n_bins, int *bin_start, cudaStream_t st) {
+  k_bin_starts<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(sorted_key, n, n_bins, bin_start);
+}
+
+__global__ void k_iota(int *v, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (int)i;
+}
+void launch_iota(int *v, long long n, cudaStream_t st) {
+  if (n <= 0) return;
+  k_iota<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, n);
+}
+
+}  // namespace mpm

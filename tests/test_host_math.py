@@ -1,0 +1,79 @@
+"""The product's device arithmetic (csrc/mpm_math.cuh), compiled for the host and run in the
+reference's sequential order, must equal the pinned oracle BIT FOR BIT -- 2D shipped scene,
+all three materials, FLIP blend, and the 3D lift.  No GPU needed; the GPU tests then only have to
+show that the kernels move the same numbers (and differ by atomic summation order alone)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle.cpu import DEFAULT_MATERIALS, make_params
+from mpm_flip98a_b200 import scenes
+from tests.hostcheck import HostCheck
+
+
+def bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.int32)
+
+
+@pytest.fixture(scope="module")
+def hc():
+    return HostCheck()
+
+
+def run_both(oracle, hc, dim, n_grid, dt, vol_p, alpha, p0, steps):
+    P = make_params(dim=dim, n_grid=n_grid, vol_p=vol_p, alpha=alpha)
+    a = p0.copy()
+    ga, ta = oracle.advance(P, dt, a, steps, want_grid=True, want_post_p2g=True)
+    H = hc.params(n_grid, 1.0, vol_p, (0.0, -200.0, 0.0), 0.05, 0.6, 20.0, alpha, DEFAULT_MATERIALS)
+    b = p0.copy()
+    gb, tb = hc.advance(H, dim, n_grid, dt, b, steps)
+    return (a, ga, ta), (b, gb, tb)
+
+
+def test_shipped_scene_bitwise(oracle, hc, shipped):
+    (a, ga, ta), (b, gb, tb) = run_both(oracle, hc, 2, 80, 1e-4, 1.0, 0.0, shipped["step0"], 300)
+    assert np.array_equal(bits(a), bits(b))
+    assert np.array_equal(bits(ga), bits(gb)) and np.array_equal(bits(ta), bits(tb))
+    # and straight against the reference's own golden state
+    (a, _, _), (b, _, _) = run_both(oracle, hc, 2, 80, 1e-4, 1.0, 0.0, shipped["step100"], 1)
+    assert np.array_equal(bits(b), bits(shipped["step101"]))
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.95])
+def test_three_materials_bitwise(oracle, hc, alpha):
+    p0 = scenes.commented_three_blocks()
+    (a, ga, ta), (b, gb, tb) = run_both(oracle, hc, 2, 80, 1e-4, 1.0, alpha, p0, 400)
+    assert np.array_equal(bits(a), bits(b))
+    assert np.array_equal(bits(ga), bits(gb)) and np.array_equal(bits(ta), bits(tb))
+    assert np.isfinite(a).all()
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.95])
+def test_3d_lift_bitwise(oracle, hc, alpha):
+    n = 24
+    dt, vol = scenes.scaled_constants(n)
+    p0 = scenes.collapse_3d(n, per_side=2, y_top=0.4, xz=(0.2, 0.8))
+    (a, ga, ta), (b, gb, tb) = run_both(oracle, hc, 3, n, dt, vol, alpha, p0, 60)
+    assert np.array_equal(bits(a), bits(b))
+    assert np.array_equal(bits(ga), bits(gb)) and np.array_equal(bits(ta), bits(tb))
+    assert np.isfinite(a).all()
+    assert np.abs(a[:, 3:6]).max() > 0.01  # it actually moved
+
+
+def test_decompositions_bitwise(hc, decomp2, oracle):
+    L = hc.lib
+    for m, pol, svd in zip(decomp2["m"], decomp2["polar"], decomp2["svd"]):
+        m = np.ascontiguousarray(m)
+        R, S, U, sg, V = (np.zeros(4, np.float32) for _ in range(5))
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        L.hostcheck_polar2(vp(m), vp(R), vp(S))
+        L.hostcheck_svd2(vp(m), vp(U), vp(sg), vp(V))
+        assert np.array_equal(bits(np.concatenate([R, S])), bits(pol))
+        assert np.array_equal(bits(np.concatenate([U, sg, V])), bits(svd))
+    rs = np.random.RandomState(3)
+    for m in (np.eye(3).reshape(1, 9) + 0.05 * rs.randn(200, 9)).astype(np.float32):
+        U, V, s = np.zeros(9, np.float32), np.zeros(9, np.float32), np.zeros(3, np.float32)
+        L.hostcheck_svd3(vp(m), vp(U), vp(s), vp(V))
+        Uo, so, Vo = oracle.svd3(m)
+        assert np.array_equal(bits(np.concatenate([U, s, V])), bits(np.concatenate([Uo, so, Vo])))
