@@ -163,6 +163,7 @@ def main():
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--naive", action="store_true", help="one-thread-per-particle kernels (MPM_FLAG_NAIVE)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--rebin-every", type=int, default=0, help="storage re-sort interval (0 = engine default)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -197,7 +198,7 @@ def main():
     flags = FLAG_NAIVE if args.naive else 0
     with torch.cuda.stream(stream):
         eng = mpm.Engine(dim=dim, n_grid=n_grid, capacity=n, dt=dt, vol_p=vol, alpha=alpha, device=local,
-                         flags=flags, stream=stream.cuda_stream)
+                         flags=flags, stream=stream.cuda_stream, rebin_every=args.rebin_every)
         eng.lib.mpm_upload_particles(eng.h, host.data_ptr(), n, 0)
         eng.substep(args.warm_substeps)
         eng.synchronize()

@@ -134,6 +134,8 @@ typedef struct mpm_profile {
   double ms[MPM_PHASE_COUNT];          /* device milliseconds per phase since mpm_profile_enable */
   long long launches[MPM_PHASE_COUNT]; /* kernels launched per phase (memsets/copies not counted) */
   long long substeps;
+  long long fallback_particles; /* binned P2G: particles that had drifted past the bin margin and
+                                   took the per-particle scatter instead (correct, just slower) */
 } mpm_profile;
 int mpm_profile_enable(mpm_handle *h, int on); /* (re)starts accumulation from zero */
 int mpm_profile_read(mpm_handle *h, mpm_profile *out); /* synchronises */

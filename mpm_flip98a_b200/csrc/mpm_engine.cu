@@ -48,6 +48,8 @@ struct mpm_handle {
   bool tap_valid = false;
 
   int *status_dev = nullptr;
+  unsigned long long *stats_dev = nullptr;  // [0] = binned-P2G fallback particles
+  bool binned = false;                      // CTA-per-bin P2G (default) vs MPM_FLAG_NAIVE
   int status_host_sticky = 0;
 
   // binning
@@ -231,6 +233,8 @@ int mpm_handle::init() {
     if ((rc = dalloc(&grid_tap, (size_t)nodes))) return rc;
   if ((rc = dalloc(&status_dev, 4))) return rc;
   MPM_CUDA(cudaMemsetAsync(status_dev, 0, 16, stream));
+  if ((rc = dalloc(&stats_dev, 4))) return rc;
+  MPM_CUDA(cudaMemsetAsync(stats_dev, 0, 32, stream));
 
   for (int b = 0; b < 2; b++) {
     if (D == 2) {
@@ -256,6 +260,7 @@ int mpm_handle::init() {
   if ((rc = dalloc(&sb.hist, sort_hist_elems(cap)))) return rc;
   if ((rc = dalloc(&sb.scan_tmp, scan_tmp_elems((long long)sort_hist_elems(cap))))) return rc;
   if ((rc = dalloc(&bin_start, (size_t)G.n_bins + 1))) return rc;
+  binned = !(cfg.flags & MPM_FLAG_NAIVE) && (D == 2 ? p2g_cells_supported<2>(G) : p2g_cells_supported<3>(G));
 
   stage_records = cap < (1LL << 22) ? cap : (1LL << 22);  // <= 4M records (224 / 416 MB) per chunk
   if ((rc = dalloc(&stage, (size_t)stage_records * record_words()))) return rc;
@@ -338,8 +343,13 @@ int mpm_handle::step_p2g(float dt) {
     MPM_CUDA(cudaMemsetAsync(grid, 0, (size_t)nodes * sizeof(float4), stream));  // :50
   }
   Phase ph(this, MPM_PHASE_P2G, n > 0 ? 1 : 0);
-  if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], n, gp<2>(), status_dev, stream);
-  else launch_p2g_naive<3>(P, dt, s3[cur], n, gp<3>(), status_dev, stream);
+  if (binned) {
+    if (D == 2) launch_p2g_cells<2>(P, G, dt, s2[cur], n, bin_start, gp<2>(), status_dev, stats_dev, stream);
+    else launch_p2g_cells<3>(P, G, dt, s3[cur], n, bin_start, gp<3>(), status_dev, stats_dev, stream);
+  } else {
+    if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], n, gp<2>(), status_dev, stream);
+    else launch_p2g_naive<3>(P, dt, s3[cur], n, gp<3>(), status_dev, stream);
+  }
   return MPM_OK;
 }
 
@@ -369,7 +379,7 @@ int mpm_handle::substep(float dt, int n_steps) {
   }
   MPM_CUDA(cudaSetDevice(cfg.device));
   if (!(dt > 0)) dt = cfg.dt;
-  int every = cfg.rebin_every == 0 ? 32 : cfg.rebin_every;
+  int every = cfg.rebin_every == 0 ? (binned ? 16 : 32) : cfg.rebin_every;
   for (int s = 0; s < n_steps; s++) {
     int rc;
     if (every > 0 && steps_since_sort >= every)
@@ -553,6 +563,7 @@ int mpm_profile_enable(mpm_handle *h, int on) {
   cudaStreamSynchronize(h->stream);
   h->flush_spans();
   memset(&h->prof, 0, sizeof h->prof);
+  cudaMemsetAsync(h->stats_dev, 0, 32, h->stream);
   h->prof_on = on != 0;
   return MPM_OK;
 }
@@ -565,6 +576,9 @@ int mpm_profile_read(mpm_handle *h, mpm_profile *out) {
     return MPM_E_CUDA;
   }
   h->flush_spans();
+  unsigned long long st[4] = {0, 0, 0, 0};
+  cudaMemcpy(st, h->stats_dev, sizeof st, cudaMemcpyDeviceToHost);
+  h->prof.fallback_particles = (long long)st[0];
   *out = h->prof;
   return MPM_OK;
 }

@@ -89,6 +89,250 @@ template void launch_p2g_naive<2>(const Params &, float, const SoA<2> &, long lo
 template void launch_p2g_naive<3>(const Params &, float, const SoA<3> &, long long, GridPtrs<3>, int *, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
+// binned P2G ("cell gather"): one CTA per bin of B^D cells.  No floating-point atomics in shared
+// memory (on sm_100a atomicAdd(float) on shared is a CAS loop, ATOMS.CAST.SPIN) and no shuffles:
+//   phase 1  thread per particle (coalesced SoA loads): stencil, stress, affine (:55-89) -> a compact
+//            record (fx, mass*v, affine) in shared memory; an integer counting sort by local cell
+//            (native ATOMS.ADD) orders the records by the cell of their base node;
+//   phase 2  thread per (cell[, stencil row]): walks its cell's records, forms the very same node
+//            contributions as :92-100 (p2g_node_value) and sums them in REGISTERS -- every particle of
+//            a cell hits the same 3^D nodes -- then issues one vector RED per (cell, node).
+// Global atomics drop from 3^D per particle to 3^D per occupied cell.  Bin membership may be stale
+// (storage is re-sorted every few substeps): the local cell grid carries a 1-cell margin and a
+// particle that drifted further falls back to per-particle REDs, so the result never depends on it.
+// ------------------------------------------------------------------------------------------------
+template <int D>
+struct CellRec;
+template <>
+struct CellRec<2> {
+  float4 a, b;  // fx.x fx.y mv.x mv.y | A00 A10 A01 A11 (column-major d[c][r])
+};
+template <>
+struct CellRec<3> {
+  float4 a, b, c, d;  // fx.xyz mv.x | mv.y mv.z A[0][0] A[0][1] | A[0][2] A[1][0..2] | A[2][0..2] pad
+};
+
+template <int D>
+__device__ __forceinline__ void pack_rec(CellRec<D> &r, const float *fx, const float *mv, const Mat<D> &A);
+template <>
+__device__ __forceinline__ void pack_rec<2>(CellRec<2> &r, const float *fx, const float *mv, const Mat<2> &A) {
+  r.a = make_float4(fx[0], fx[1], mv[0], mv[1]);
+  r.b = make_float4(A.d[0][0], A.d[0][1], A.d[1][0], A.d[1][1]);
+}
+template <>
+__device__ __forceinline__ void pack_rec<3>(CellRec<3> &r, const float *fx, const float *mv, const Mat<3> &A) {
+  r.a = make_float4(fx[0], fx[1], fx[2], mv[0]);
+  r.b = make_float4(mv[1], mv[2], A.d[0][0], A.d[0][1]);
+  r.c = make_float4(A.d[0][2], A.d[1][0], A.d[1][1], A.d[1][2]);
+  r.d = make_float4(A.d[2][0], A.d[2][1], A.d[2][2], 0.0f);
+}
+template <int D>
+__device__ __forceinline__ void unpack_rec(const CellRec<D> &r, float *fx, float *mv, Mat<D> &A);
+template <>
+__device__ __forceinline__ void unpack_rec<2>(const CellRec<2> &r, float *fx, float *mv, Mat<2> &A) {
+  fx[0] = r.a.x; fx[1] = r.a.y; mv[0] = r.a.z; mv[1] = r.a.w;
+  A.d[0][0] = r.b.x; A.d[0][1] = r.b.y; A.d[1][0] = r.b.z; A.d[1][1] = r.b.w;
+}
+template <>
+__device__ __forceinline__ void unpack_rec<3>(const CellRec<3> &r, float *fx, float *mv, Mat<3> &A) {
+  fx[0] = r.a.x; fx[1] = r.a.y; fx[2] = r.a.z; mv[0] = r.a.w;
+  mv[1] = r.b.x; mv[2] = r.b.y; A.d[0][0] = r.b.z; A.d[0][1] = r.b.w;
+  A.d[0][2] = r.c.x; A.d[1][0] = r.c.y; A.d[1][1] = r.c.z; A.d[1][2] = r.c.w;
+  A.d[2][0] = r.d.x; A.d[2][1] = r.d.y; A.d[2][2] = r.d.z;
+}
+
+template <int D>
+__device__ __forceinline__ void red_node(const Params &P, float4 *grid, int i, int j, int k, const float *nv) {
+  long long node = node_index<D>(P, i, j, k);
+  float4 val = make_float4(nv[0], nv[1], nv[2], D == 3 ? nv[D] : 0.0f);
+  atomicAdd(&grid[node], val);  // RED.E.ADD.F32x4
+}
+
+// B = bin edge in cells, NT = threads, CAP = records per shared-memory chunk,
+// TPC = threads per cell in phase 2 (1: all 3^D nodes; 3: one stencil row `a` each)
+template <int D, int B, int NT, int CAP, int TPC>
+__global__ void __launch_bounds__(NT) k_p2g_cells(Params P, BinGeom G, float dt, SoA<D> s,
+                                                  const int *__restrict__ bin_start, float4 *__restrict__ grid,
+                                                  int *__restrict__ status, unsigned long long *__restrict__ stats) {
+  constexpr int M = 1, L = B + 2 * M;
+  constexpr int NC = D == 2 ? L * L : L * L * L;
+  __shared__ CellRec<D> rec[CAP];
+  __shared__ unsigned short cell_of[CAP], rank_of[CAP], sorted[CAP];
+  __shared__ int cnt[NC + 1];
+  const int tid = threadIdx.x;
+  const int bin = blockIdx.x;
+  const int s0 = bin_start[bin], s1 = bin_start[bin + 1];
+  if (s0 == s1) return;
+  // bin coordinates -> origin (global cell index of local cell 0, i.e. bin origin minus the margin)
+  int o[3] = {0, 0, 0};
+  {
+    int r = bin;
+    if (D == 3) { o[2] = (r % G.nb[2]) * B - M; r /= G.nb[2]; }
+    o[1] = (r % G.nb[1]) * B - M;
+    o[0] = (r / G.nb[1]) * B + P.slab_lo - M;
+  }
+  unsigned n_fallback = 0;
+  for (int c0 = s0; c0 < s1; c0 += CAP) {
+    const int m = min(CAP, s1 - c0);
+    for (int k = tid; k <= NC; k += NT) cnt[k] = 0;
+    __syncthreads();
+    // ---- phase 1: thread per particle ----
+    for (int i = tid; i < m; i += NT) {
+      PState<D> p;
+      load_full(s, (long long)c0 + i, p);
+      Stencil<D> st = make_stencil<D>(p.x, P.inv_dx);
+      int bad = clamp_base<D>(P, st.base);
+      if (bad) atomicOr(status, bad);
+      const Material &mat = P.mat[material_index(P, p.mat)];
+      Mat<D> affine = p2g_affine<D>(P, mat, dt, p.F, p.C, p.Jp);
+      float mv[D];
+#pragma unroll
+      for (int c = 0; c < D; c++) mv[c] = P.mass_p * p.v[c];
+      int l[3] = {st.base[0] - o[0], st.base[1] - o[1], D == 3 ? st.base[D - 1] - o[2] : 0};
+      bool inside = (unsigned)l[0] < (unsigned)L && (unsigned)l[1] < (unsigned)L && (D == 2 || (unsigned)l[2] < (unsigned)L);
+      if (inside) {
+        int cell = l[0] * L + l[1];
+        if (D == 3) cell = cell * L + l[2];
+        int r = atomicAdd(&cnt[cell], 1);
+        cell_of[i] = (unsigned short)cell;
+        rank_of[i] = (unsigned short)r;
+        pack_rec<D>(rec[i], st.fx, mv, affine);
+      } else {  // drifted past the margin since the last re-sort: plain per-particle scatter
+        cell_of[i] = 0xffffu;
+        n_fallback++;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int c = 0; c < (D == 3 ? 3 : 1); c++) {
+              float nv[D + 1];
+              p2g_node_value<D>(P, st, affine, mv, a, b, c, nv);
+              red_node<D>(P, grid, st.base[0] + a, st.base[1] + b, D == 3 ? st.base[D - 1] + c : 0, nv);
+            }
+      }
+    }
+    __syncthreads();
+    // ---- exclusive scan of the cell counts (NC <= 216): warp 0, 32 cells per round ----
+    if (tid < 32) {
+      int run = 0;
+      for (int k0 = 0; k0 < NC; k0 += 32) {
+        int k = k0 + tid;
+        int v = k < NC ? cnt[k] : 0;
+        int inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, inc, d);
+          if (tid >= d) inc += t;
+        }
+        if (k < NC) cnt[k] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+      }
+      if (tid == 0) cnt[NC] = run;
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += NT) {
+      unsigned c = cell_of[i];
+      if (c != 0xffffu) sorted[cnt[c] + rank_of[i]] = (unsigned short)i;
+    }
+    __syncthreads();
+    // ---- phase 2: thread per (cell, stencil row) ----
+    for (int item = tid; item < NC * TPC; item += NT) {
+      const int cell = item / TPC;
+      const int a_lo = TPC == 1 ? 0 : item % TPC, a_n = TPC == 1 ? 3 : 1;
+      const int n0 = cnt[cell], n1 = cnt[cell + 1];
+      if (n0 == n1) continue;
+      constexpr int NB = D == 3 ? 3 : 1;
+      float acc[3][3][NB][D + 1];
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+#pragma unroll
+          for (int c = 0; c < NB; c++)
+#pragma unroll
+            for (int q = 0; q <= D; q++) acc[a][b][c][q] = 0.0f;
+      for (int jj = n0; jj < n1; jj++) {
+        const int i = sorted[jj];
+        Stencil<D> st;
+        float mv[D];
+        Mat<D> affine;
+        unpack_rec<D>(rec[i], st.fx, mv, affine);
+#pragma unroll
+        for (int k = 0; k < D; k++) {  // the same three expressions as make_stencil (:61-63)
+          st.w[0][k] = 0.5f * ((1.5f - st.fx[k]) * (1.5f - st.fx[k]));
+          st.w[1][k] = 0.75f - ((st.fx[k] - 1.0f) * (st.fx[k] - 1.0f));
+          st.w[2][k] = 0.5f * ((st.fx[k] - 0.5f) * (st.fx[k] - 0.5f));
+        }
+#pragma unroll
+        for (int aa = 0; aa < 3; aa++) {
+          if (aa >= a_n) break;
+          const int a = TPC == 1 ? aa : a_lo;
+#pragma unroll
+          for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int c = 0; c < NB; c++) {
+              float nv[D + 1];
+              if (TPC == 1) {
+                p2g_node_value<D>(P, st, affine, mv, aa, b, c, nv);
+              } else {
+                // `a` is a per-lane runtime value: select its weight and shift fx instead of indexing
+                // registers dynamically.  Bit-exact: ((float)a - fx) == (0.0f - (fx - (float)a)) because
+                // round-to-nearest is symmetric, so dpos (:94) is the identical float.
+                Stencil<D> sa = st;
+                sa.w[0][0] = a == 0 ? st.w[0][0] : (a == 1 ? st.w[1][0] : st.w[2][0]);
+                sa.fx[0] = st.fx[0] - (float)a;
+                p2g_node_value<D>(P, sa, affine, mv, 0, b, c, nv);
+              }
+#pragma unroll
+              for (int q = 0; q <= D; q++) acc[aa][b][c][q] = acc[aa][b][c][q] + nv[q];
+            }
+        }
+      }
+      // cell coordinates -> global node of stencil offset (0,0,0)
+      int lc[3];
+      {
+        int r = cell;
+        if (D == 3) { lc[2] = r % L; r /= L; } else lc[2] = 0;
+        lc[1] = r % L;
+        lc[0] = r / L;
+      }
+#pragma unroll
+      for (int aa = 0; aa < 3; aa++) {
+        if (aa >= a_n) break;
+        const int a = TPC == 1 ? aa : a_lo;
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+#pragma unroll
+          for (int c = 0; c < NB; c++)
+            red_node<D>(P, grid, o[0] + lc[0] + a, o[1] + lc[1] + b, D == 3 ? o[2] + lc[2] + c : 0, acc[aa][b][c]);
+      }
+    }
+    __syncthreads();
+  }
+  if (stats && n_fallback) atomicAdd(&stats[0], (unsigned long long)n_fallback);
+}
+
+template <int D>
+bool p2g_cells_supported(const BinGeom &G) {
+  return G.edge == (D == 2 ? 8 : 4);
+}
+template bool p2g_cells_supported<2>(const BinGeom &);
+template bool p2g_cells_supported<3>(const BinGeom &);
+
+template <int D>
+void launch_p2g_cells(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, long long n, const int *bin_start,
+                      GridPtrs<D> g, int *status, unsigned long long *stats, cudaStream_t st) {
+  if (n <= 0) return;
+  if constexpr (D == 2) k_p2g_cells<2, 8, 128, 768, 1><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+  else k_p2g_cells<3, 4, 128, 512, 3><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+}
+template void launch_p2g_cells<2>(const Params &, const BinGeom &, float, const SoA<2> &, long long, const int *,
+                                  GridPtrs<2>, int *, unsigned long long *, cudaStream_t);
+template void launch_p2g_cells<3>(const Params &, const BinGeom &, float, const SoA<3> &, long long, const int *,
+                                  GridPtrs<3>, int *, unsigned long long *, cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
 // naive G2P: one thread per particle, 3^D node reads through the read-only path, in-place update.
 // ------------------------------------------------------------------------------------------------
 template <int D>

@@ -5,6 +5,11 @@
 
 namespace mpm {
 
+struct BinGeom {
+  int edge;      // cells per bin edge
+  int nb[3];     // bins per axis (x: over the owned slab)
+  int n_bins;
+};
 template <int D>
 struct GridPtrs {
   float4 *g;     // node array (see mpm_common.cuh)
@@ -21,6 +26,13 @@ void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long n, G
 template <int D>
 void launch_grid_update(const Params &P, float dt, GridPtrs<D> g, cudaStream_t st);
 
+// ---- binned path: one CTA per bin, in-CTA cell sort + register accumulation (see mpm_kernels.cu) --
+template <int D>
+bool p2g_cells_supported(const BinGeom &G);
+template <int D>
+void launch_p2g_cells(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, long long n, const int *bin_start,
+                      GridPtrs<D> g, int *status, unsigned long long *stats, cudaStream_t st);
+
 // ---- AoS <-> SoA at the C-ABI ------------------------------------------------------------------
 // records [first, first+count) of the caller's AoS -> SoA slots [first, first+count), id = index
 template <int D>
@@ -33,11 +45,6 @@ template <int D>
 void launch_reorder(const SoA<D> &src, const SoA<D> &dst, const int *order, long long n, cudaStream_t st);
 
 // ---- binning -----------------------------------------------------------------------------------
-struct BinGeom {
-  int edge;      // cells per bin edge
-  int nb[3];     // bins per axis (x: over the owned slab)
-  int n_bins;
-};
 BinGeom make_bin_geom(const Params &P, int dim, int edge);
 // cell[n*D] (may be NULL), key[n]; flags STATUS_DOMAIN
 template <int D>

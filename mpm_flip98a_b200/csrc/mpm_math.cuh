@@ -299,7 +299,15 @@ struct Stencil {
   float w[3][D];
 };
 
-MPM_HD int base_coord(float x, float inv_dx) { return (int)(x * inv_dx - 0.5f); }
+// never contracted into an FMA, whatever -fmad says: the integer cell must be bit-exact
+#if defined(__CUDA_ARCH__)
+#define MPM_MUL_RN(a, b) __fmul_rn((a), (b))
+#define MPM_SUB_RN(a, b) __fsub_rn((a), (b))
+#else
+#define MPM_MUL_RN(a, b) ((a) * (b))
+#define MPM_SUB_RN(a, b) ((a) - (b))
+#endif
+MPM_HD int base_coord(float x, float inv_dx) { return (int)MPM_SUB_RN(MPM_MUL_RN(x, inv_dx), 0.5f); }
 
 template <int D>
 MPM_HD Stencil<D> make_stencil(const float *x, float inv_dx) {
@@ -307,7 +315,7 @@ MPM_HD Stencil<D> make_stencil(const float *x, float inv_dx) {
 #pragma unroll
   for (int k = 0; k < D; k++) {
     s.base[k] = base_coord(x[k], inv_dx);       // :55
-    s.fx[k] = x[k] * inv_dx - (float)s.base[k];  // :57
+    s.fx[k] = MPM_SUB_RN(MPM_MUL_RN(x[k], inv_dx), (float)s.base[k]);  // :57
     s.w[0][k] = 0.5f * ((1.5f - s.fx[k]) * (1.5f - s.fx[k]));       // :61
     s.w[1][k] = 0.75f - ((s.fx[k] - 1.0f) * (s.fx[k] - 1.0f));      // :62
     s.w[2][k] = 0.5f * ((s.fx[k] - 0.5f) * (s.fx[k] - 0.5f));       // :63

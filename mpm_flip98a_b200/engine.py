@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmpm.so")
+LIB_PATH = os.environ.get("MPM_LIBRARY") or os.path.join(HERE, "libmpm.so")  # override: A/B builds only
 
 MPM_ABI_VERSION = 1
 KIND_FLUID, KIND_JELLY, KIND_SNOW = 0, 1, 2
@@ -55,7 +55,8 @@ class MigrationDesc(ctypes.Structure):
 
 
 class Profile(ctypes.Structure):
-    _fields_ = [("ms", ctypes.c_double * 8), ("launches", ctypes.c_longlong * 8), ("substeps", ctypes.c_longlong)]
+    _fields_ = [("ms", ctypes.c_double * 8), ("launches", ctypes.c_longlong * 8), ("substeps", ctypes.c_longlong),
+                ("fallback_particles", ctypes.c_longlong)]
 
 
 PHASES = ("clear", "p2g", "grid", "g2p", "bin", "halo", "migrate")
@@ -215,6 +216,7 @@ class Engine:
         self._check(self.lib.mpm_profile_read(self.h, ctypes.byref(pr)))
         out = {name: (pr.ms[i], pr.launches[i]) for i, name in enumerate(PHASES)}
         out["substeps"] = pr.substeps
+        out["fallback_particles"] = pr.fallback_particles
         return out
 
     def grid_shape(self):
