@@ -50,8 +50,11 @@ typedef struct mpm_material {
 
 enum {
   MPM_FLAG_CAPTURE_POST_P2G = 1 << 0, /* keep a copy of the grid between P2G and the grid update */
-  MPM_FLAG_NAIVE = 1 << 1             /* one-thread-per-particle kernels with global atomics
+  MPM_FLAG_NAIVE = 1 << 1,            /* one-thread-per-particle kernels with global atomics
                                          (no binning); the small-scene / debugging path */
+  MPM_FLAG_STRICT = 1 << 2            /* binned P2G forms every node contribution in the reference's
+                                         exact association order (:92-100) instead of the separable
+                                         FMA form (algebraically identical, ~1e-7 relative apart) */
 };
 
 /* Everything the reference fixes at compile time (:8-26, :113, :116, :169, :175) plus the

@@ -343,9 +343,10 @@ int mpm_handle::step_p2g(float dt) {
     MPM_CUDA(cudaMemsetAsync(grid, 0, (size_t)nodes * sizeof(float4), stream));  // :50
   }
   Phase ph(this, MPM_PHASE_P2G, n > 0 ? 1 : 0);
+  const bool strict = (cfg.flags & MPM_FLAG_STRICT) != 0;
   if (binned) {
-    if (D == 2) launch_p2g_cells<2>(P, G, dt, s2[cur], n, bin_start, gp<2>(), status_dev, stats_dev, stream);
-    else launch_p2g_cells<3>(P, G, dt, s3[cur], n, bin_start, gp<3>(), status_dev, stats_dev, stream);
+    if (D == 2) launch_p2g_cells<2>(P, G, dt, s2[cur], n, bin_start, gp<2>(), status_dev, stats_dev, strict, stream);
+    else launch_p2g_cells<3>(P, G, dt, s3[cur], n, bin_start, gp<3>(), status_dev, stats_dev, strict, stream);
   } else {
     if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], n, gp<2>(), status_dev, stream);
     else launch_p2g_naive<3>(P, dt, s3[cur], n, gp<3>(), status_dev, stream);

@@ -150,8 +150,11 @@ __device__ __forceinline__ void red_node(const Params &P, float4 *grid, int i, i
 
 // B = bin edge in cells, NT = threads, CAP = records per shared-memory chunk,
 // TPC = threads per cell in phase 2 (1: all 3^D nodes; 3: one stencil row `a` each)
-template <int D, int B, int NT, int CAP, int TPC>
-__global__ void __launch_bounds__(NT) k_p2g_cells(Params P, BinGeom G, float dt, SoA<D> s,
+#ifndef MPM_P2G_MINB
+#define MPM_P2G_MINB 8
+#endif
+template <int D, int B, int NT, int CAP, int TPC, bool FAST>
+__global__ void __launch_bounds__(NT, MPM_P2G_MINB) k_p2g_cells(Params P, BinGeom G, float dt, SoA<D> s,
                                                   const int *__restrict__ bin_start, float4 *__restrict__ grid,
                                                   int *__restrict__ status, unsigned long long *__restrict__ stats) {
   constexpr int M = 1, L = B + 2 * M;
@@ -159,6 +162,11 @@ __global__ void __launch_bounds__(NT) k_p2g_cells(Params P, BinGeom G, float dt,
   __shared__ CellRec<D> rec[CAP];
   __shared__ unsigned short cell_of[CAP], rank_of[CAP], sorted[CAP];
   __shared__ int cnt[NC + 1];
+  // phase-2 work items: (cell, first record, record count); a cell with more than RM records is
+  // split evenly so that the lanes of a warp walk runs of similar length
+  constexpr int RM = 8, MAXI = NC + CAP / RM + 1;
+  __shared__ int item_first[NC + 1];              // per cell: index of its first item (exclusive scan)
+  __shared__ unsigned short item_cell[MAXI];
   const int tid = threadIdx.x;
   const int bin = blockIdx.x;
   const int s0 = bin_start[bin], s1 = bin_start[bin + 1];
@@ -213,35 +221,52 @@ __global__ void __launch_bounds__(NT) k_p2g_cells(Params P, BinGeom G, float dt,
       }
     }
     __syncthreads();
-    // ---- exclusive scan of the cell counts (NC <= 216): warp 0, 32 cells per round ----
+    // ---- exclusive scans (NC <= 216) by warp 0, 32 cells per round: record starts and item starts ----
     if (tid < 32) {
-      int run = 0;
+      int run = 0, irun = 0;
       for (int k0 = 0; k0 < NC; k0 += 32) {
         int k = k0 + tid;
         int v = k < NC ? cnt[k] : 0;
-        int inc = v;
+        int iv = (v + RM - 1) / RM;  // items of this cell
+        int inc = v, iinc = iv;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
           int t = __shfl_up_sync(0xffffffffu, inc, d);
-          if (tid >= d) inc += t;
+          int u = __shfl_up_sync(0xffffffffu, iinc, d);
+          if (tid >= d) { inc += t; iinc += u; }
         }
-        if (k < NC) cnt[k] = run + inc - v;
+        if (k < NC) {
+          cnt[k] = run + inc - v;
+          item_first[k] = irun + iinc - iv;
+        }
         run += __shfl_sync(0xffffffffu, inc, 31);
+        irun += __shfl_sync(0xffffffffu, iinc, 31);
       }
-      if (tid == 0) cnt[NC] = run;
+      if (tid == 0) { cnt[NC] = run; item_first[NC] = irun; }
     }
     __syncthreads();
+    for (int k = tid; k < NC; k += NT)
+      for (int it = item_first[k]; it < item_first[k + 1]; it++) item_cell[it] = (unsigned short)k;
     for (int i = tid; i < m; i += NT) {
       unsigned c = cell_of[i];
       if (c != 0xffffu) sorted[cnt[c] + rank_of[i]] = (unsigned short)i;
     }
     __syncthreads();
     // ---- phase 2: thread per (cell, stencil row) ----
-    for (int item = tid; item < NC * TPC; item += NT) {
-      const int cell = item / TPC;
-      const int a_lo = TPC == 1 ? 0 : item % TPC, a_n = TPC == 1 ? 3 : 1;
-      const int n0 = cnt[cell], n1 = cnt[cell + 1];
-      if (n0 == n1) continue;
+    const int n_items = item_first[NC];
+    for (int item = tid; item < n_items * TPC; item += NT) {
+      // TPC == 3: a-major numbering (all items for row 0, then row 1, ...) keeps `a` warp-uniform
+      const int it = TPC == 1 ? item : item % n_items;
+      const int a_lo = TPC == 1 ? 0 : item / n_items, a_n = TPC == 1 ? 3 : 1;
+      const int cell = item_cell[it];
+      int n0, n1;
+      {
+        const int c0r = cnt[cell], k = cnt[cell + 1] - c0r;
+        const int parts = item_first[cell + 1] - item_first[cell], sub = it - item_first[cell];
+        const int per = (k + parts - 1) / parts;  // even split
+        n0 = c0r + sub * per;
+        n1 = min(n0 + per, c0r + k);
+      }
       constexpr int NB = D == 3 ? 3 : 1;
       float acc[3][3][NB][D + 1];
 #pragma unroll
@@ -264,29 +289,77 @@ __global__ void __launch_bounds__(NT) k_p2g_cells(Params P, BinGeom G, float dt,
           st.w[1][k] = 0.75f - ((st.fx[k] - 1.0f) * (st.fx[k] - 1.0f));
           st.w[2][k] = 0.5f * ((st.fx[k] - 0.5f) * (st.fx[k] - 0.5f));
         }
+        if (FAST) {
+          // Separable form of :92-100 with explicit FMAs: w*(mv + A*((o - fx)*dx)) == w*(q + sum_k o_k*cs_k),
+          // cs_k = A.col(k)*dx, q = mv - sum_k cs_k*fx_k.  Algebraically identical, ~2.5x fewer
+          // instructions; rounding differs from the reference's association at the 1e-7 level
+          // (the same size as its own summation-order noise).  MPM_FLAG_STRICT keeps the exact form.
+          float cs[D][D], q[D];
 #pragma unroll
-        for (int aa = 0; aa < 3; aa++) {
-          if (aa >= a_n) break;
-          const int a = TPC == 1 ? aa : a_lo;
+          for (int k = 0; k < D; k++)
 #pragma unroll
-          for (int b = 0; b < 3; b++)
+            for (int r = 0; r < D; r++) cs[k][r] = affine.d[k][r] * P.dx;
 #pragma unroll
-            for (int c = 0; c < NB; c++) {
-              float nv[D + 1];
-              if (TPC == 1) {
-                p2g_node_value<D>(P, st, affine, mv, aa, b, c, nv);
-              } else {
-                // `a` is a per-lane runtime value: select its weight and shift fx instead of indexing
-                // registers dynamically.  Bit-exact: ((float)a - fx) == (0.0f - (fx - (float)a)) because
-                // round-to-nearest is symmetric, so dpos (:94) is the identical float.
-                Stencil<D> sa = st;
-                sa.w[0][0] = a == 0 ? st.w[0][0] : (a == 1 ? st.w[1][0] : st.w[2][0]);
-                sa.fx[0] = st.fx[0] - (float)a;
-                p2g_node_value<D>(P, sa, affine, mv, 0, b, c, nv);
+          for (int r = 0; r < D; r++) {
+            q[r] = mv[r];
+#pragma unroll
+            for (int k = 0; k < D; k++) q[r] = __fmaf_rn(-cs[k][r], st.fx[k], q[r]);
+          }
+#pragma unroll
+          for (int aa = 0; aa < 3; aa++) {
+            if (aa >= a_n) break;
+            const int a = TPC == 1 ? aa : a_lo;
+            const float wa = TPC == 1 ? st.w[aa][0] : (a == 0 ? st.w[0][0] : (a == 1 ? st.w[1][0] : st.w[2][0]));
+            float xa[D];
+#pragma unroll
+            for (int r = 0; r < D; r++) xa[r] = __fmaf_rn((float)a, cs[0][r], q[r]);
+#pragma unroll
+            for (int b = 0; b < 3; b++) {
+              const float wab = wa * st.w[b][1];
+              float yb[D];
+#pragma unroll
+              for (int r = 0; r < D; r++) yb[r] = __fmaf_rn((float)b, cs[1][r], xa[r]);
+#pragma unroll
+              for (int c = 0; c < NB; c++) {
+                float wabc = wab, zc[D];
+#pragma unroll
+                for (int r = 0; r < D; r++) zc[r] = yb[r];
+                if (D == 3) {
+                  wabc = wab * st.w[c][D - 1];
+#pragma unroll
+                  for (int r = 0; r < D; r++) zc[r] = __fmaf_rn((float)c, cs[D - 1][r], yb[r]);
+                }
+#pragma unroll
+                for (int r = 0; r < D; r++) acc[aa][b][c][r] = __fmaf_rn(wabc, zc[r], acc[aa][b][c][r]);
+                acc[aa][b][c][D] = __fmaf_rn(wabc, P.mass_p, acc[aa][b][c][D]);
               }
-#pragma unroll
-              for (int q = 0; q <= D; q++) acc[aa][b][c][q] = acc[aa][b][c][q] + nv[q];
             }
+          }
+        } else {
+  #pragma unroll
+          for (int aa = 0; aa < 3; aa++) {
+            if (aa >= a_n) break;
+            const int a = TPC == 1 ? aa : a_lo;
+  #pragma unroll
+            for (int b = 0; b < 3; b++)
+  #pragma unroll
+              for (int c = 0; c < NB; c++) {
+                float nv[D + 1];
+                if (TPC == 1) {
+                  p2g_node_value<D>(P, st, affine, mv, aa, b, c, nv);
+                } else {
+                  // `a` is a per-lane runtime value: select its weight and shift fx instead of indexing
+                  // registers dynamically.  Bit-exact: ((float)a - fx) == (0.0f - (fx - (float)a)) because
+                  // round-to-nearest is symmetric, so dpos (:94) is the identical float.
+                  Stencil<D> sa = st;
+                  sa.w[0][0] = a == 0 ? st.w[0][0] : (a == 1 ? st.w[1][0] : st.w[2][0]);
+                  sa.fx[0] = st.fx[0] - (float)a;
+                  p2g_node_value<D>(P, sa, affine, mv, 0, b, c, nv);
+                }
+  #pragma unroll
+                for (int q = 0; q <= D; q++) acc[aa][b][c][q] = acc[aa][b][c][q] + nv[q];
+              }
+          }
         }
       }
       // cell coordinates -> global node of stencil offset (0,0,0)
@@ -322,15 +395,20 @@ template bool p2g_cells_supported<3>(const BinGeom &);
 
 template <int D>
 void launch_p2g_cells(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, long long n, const int *bin_start,
-                      GridPtrs<D> g, int *status, unsigned long long *stats, cudaStream_t st) {
+                      GridPtrs<D> g, int *status, unsigned long long *stats, bool strict, cudaStream_t st) {
   if (n <= 0) return;
-  if constexpr (D == 2) k_p2g_cells<2, 8, 128, 768, 1><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
-  else k_p2g_cells<3, 4, 128, 512, 3><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+  if constexpr (D == 2) {
+    if (strict) k_p2g_cells<2, 8, 128, 768, 1, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+    else k_p2g_cells<2, 8, 128, 768, 1, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+  } else {
+    if (strict) k_p2g_cells<3, 4, 128, 512, 3, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+    else k_p2g_cells<3, 4, 128, 512, 3, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+  }
 }
 template void launch_p2g_cells<2>(const Params &, const BinGeom &, float, const SoA<2> &, long long, const int *,
-                                  GridPtrs<2>, int *, unsigned long long *, cudaStream_t);
+                                  GridPtrs<2>, int *, unsigned long long *, bool, cudaStream_t);
 template void launch_p2g_cells<3>(const Params &, const BinGeom &, float, const SoA<3> &, long long, const int *,
-                                  GridPtrs<3>, int *, unsigned long long *, cudaStream_t);
+                                  GridPtrs<3>, int *, unsigned long long *, bool, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
 // naive G2P: one thread per particle, 3^D node reads through the read-only path, in-place update.

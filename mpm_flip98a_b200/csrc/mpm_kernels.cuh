@@ -31,7 +31,7 @@ template <int D>
 bool p2g_cells_supported(const BinGeom &G);
 template <int D>
 void launch_p2g_cells(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, long long n, const int *bin_start,
-                      GridPtrs<D> g, int *status, unsigned long long *stats, cudaStream_t st);
+                      GridPtrs<D> g, int *status, unsigned long long *stats, bool strict, cudaStream_t st);
 
 // ---- AoS <-> SoA at the C-ABI ------------------------------------------------------------------
 // records [first, first+count) of the caller's AoS -> SoA slots [first, first+count), id = index

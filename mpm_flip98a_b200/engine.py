@@ -16,6 +16,7 @@ MPM_ABI_VERSION = 1
 KIND_FLUID, KIND_JELLY, KIND_SNOW = 0, 1, 2
 FLAG_CAPTURE_POST_P2G = 1
 FLAG_NAIVE = 2
+FLAG_STRICT = 4
 
 _ERRORS = {-1: "MPM_E_INVALID", -2: "MPM_E_CUDA", -3: "MPM_E_CAPACITY", -4: "MPM_E_DOMAIN", -5: "MPM_E_CFL",
            -6: "MPM_E_STATE"}
