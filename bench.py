@@ -185,6 +185,9 @@ def main():
     if world > 1:
         raise SystemExit("multi-GPU slab path not built yet")
 
+    if world > 1:
+        return run_slabs(args, rank, world, local)
+
     descr, dim, n_grid, alpha = WORKLOADS[args.workload]
     p_np, dim, n_grid, alpha, dt, vol = build_scene(args.workload)
     n = len(p_np)
@@ -249,6 +252,17 @@ def main():
         assert torch.isfinite(host_out[:: max(1, n // 100000)]).all()
         eng.close()
 
+    line = make_line(args, world, n, n, words, dim, n_grid, alpha, dt, descr, ms, value, e2e_value, prof, clocks,
+                     scaling="weak", extra_config={})
+    if not args.no_cpu:
+        val, desc, _ = cpu_sample(args.workload)
+        line["cpu_baseline"] = {"value": val, "unit": "particle-substeps/s", "cores": 1, "kind": "port",
+                                "sample": desc, "host_cores_total": os.cpu_count()}
+    print(json.dumps(line), flush=True)
+
+
+def make_line(args, world, n_total, n_local, words, dim, n_grid, alpha, dt, descr, ms, value, e2e_value, prof, clocks,
+              scaling, extra_config):
     # ---- roofline of the dominant kernel ------------------------------------------------------------
     peaks = {}
     try:
@@ -259,11 +273,11 @@ def main():
     peak_kind = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)"
     a = ALGO[dim]
     algo = {"p2g": a["p2g"], "g2p": a["g2p"] + (a["flip_extra"] if alpha != 0 else 0)}
-    phases = {k: prof[k] for k in ("clear", "p2g", "grid", "g2p", "bin")}
+    phases = {k: prof[k] for k in ("clear", "p2g", "grid", "g2p", "bin", "halo", "migrate")}
     dom = max(("p2g", "g2p"), key=lambda k: phases[k][0])
     dom_ms = phases[dom][0] / max(1, prof["substeps"])
-    achieved = algo[dom] * n / (dom_ms * 1e-3) / 1e9
-    whole = (algo["p2g"] + algo["g2p"]) * value / 1e9
+    achieved = algo[dom] * n_local / (dom_ms * 1e-3) / 1e9  # per launch == this rank's particles
+    whole = (algo["p2g"] + algo["g2p"]) * value / world / 1e9  # per GPU
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
                 "algorithmic_bytes_per_particle": algo[dom], "kernel_ms": dom_ms,
@@ -272,24 +286,129 @@ def main():
                 "phase_ms_per_substep": {k: v[0] / max(1, prof["substeps"]) for k, v in phases.items()}}
     launches = int(sum(v[1] for v in phases.values()))
 
-    line = {"metric": METRIC, "value": value, "unit": "particle-substeps/s", "n_gpus": world,
+    cfg = {"workload": descr, "name": args.workload, "dim": dim, "n_grid": n_grid, "particles": n_total,
+           "alpha": alpha, "dt": dt, "path": "naive" if args.naive else "binned",
+           "warm_substeps": args.warm_substeps,
+           "l2": "state (%.1f GB per GPU) larger than L2; no flush" % (n_local * words * 4 / 1e9)
+           if n_local * words * 4 > 2.5e8 else "state fits L2 (small workload)"}
+    cfg.update(extra_config)
+    return {"metric": METRIC, "value": value, "unit": "particle-substeps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": descr, "name": args.workload, "dim": dim, "n_grid": n_grid, "particles": n,
-                       "alpha": alpha, "dt": dt, "path": "naive" if args.naive else "default",
-                       "warm_substeps": args.warm_substeps,
-                       "l2": "state (%.1f GB) larger than L2; no flush" % (n * words * 4 / 1e9)
-                       if n * words * 4 > 2.5e8 else "state fits L2 (small workload)"},
-            "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": n * words * 4,
-                    "d2h_bytes_per_step": n * words * 4, "substeps_per_step": FRAME,
-                    "call": "mpm_upload_particles + mpm_substep(%d) + mpm_read_particles, pinned host buffers" % FRAME},
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
-    if not args.no_cpu:
-        val, desc, _ = cpu_sample(args.workload)
-        line["cpu_baseline"] = {"value": val, "unit": "particle-substeps/s", "cores": 1, "kind": "port",
-                                "sample": desc, "host_cores_total": os.cpu_count()}
-    print(json.dumps(line), flush=True)
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": cfg,
+            "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": n_total * words * 4,
+                    "d2h_bytes_per_step": n_total * words * 4, "substeps_per_step": FRAME,
+                    "call": "mpm_upload_particles + %d substeps + mpm_read_particles, pinned host buffers" % FRAME},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
+            "fallback_particles": prof.get("fallback_particles", 0)}
+
+
+def run_slabs(args, rank, world, local):
+    """N > 1: one x-slab per rank (mpm_flip98a_b200/parallel.py), halo sums + migration over NCCL P2P.
+    Weak scaling: the c4 scene at n_grid = 8192*sqrt(N) (same fill fractions), so particles AND grid
+    nodes per GPU stay what one GPU has at N = 1; the domain stays the unit square."""
+    import torch
+    import torch.distributed as dist
+    import mpm_flip98a_b200 as mpm
+    from mpm_flip98a_b200 import parallel, scenes
+    from mpm_flip98a_b200.engine import FLAG_NAIVE
+    if args.workload != "c4":
+        raise SystemExit("multi-GPU bench is defined on the c4 workload")
+    descr, dim, n0, alpha = WORKLOADS["c4"]
+    align = 8 * world
+    n_grid = int(round(n0 * world ** 0.5 / align)) * align
+    dt, vol = scenes.scaled_constants(n_grid, dim)
+    slabs = parallel.partition(n_grid, world, 8)
+    lo, hi = slabs[rank]
+    dev = "cuda:%d" % local
+    # this rank's particles: generate the cell columns that can hold owned base cells, keep the owned
+    n_max = scenes.slab_fill_2d_count(n_grid, columns=(lo, hi + 1))
+    host = torch.empty((n_max, 14), dtype=torch.float32, pin_memory=True)
+    rec = scenes.slab_fill_2d(n_grid, columns=(lo, hi + 1), out=host.numpy())
+    b = parallel.base_column(rec[:, 0], n_grid)
+    keep = (b >= lo) & (b < hi)
+    n_local = int(keep.sum())
+    host.numpy()[:n_local] = rec[keep]
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    counts[rank] = n_local
+    dist.all_reduce(counts)
+    n_total = int(counts.sum())
+    first_id = int(counts[:rank].sum())
+    assert n_total < 2 ** 31, "int32 particle ids"
+    ids = torch.arange(first_id, first_id + n_local, dtype=torch.int32).pin_memory()
+    ids_out = torch.empty(int(n_local * 1.1) + 65536, dtype=torch.int32).pin_memory()
+
+    stream = torch.cuda.Stream()
+    flags = FLAG_NAIVE if args.naive else 0
+    cap = int(n_local * 1.1) + 65536
+    with torch.cuda.stream(stream):
+        eng = mpm.Engine(dim=dim, n_grid=n_grid, capacity=cap, dt=dt, vol_p=vol, alpha=alpha, device=local,
+                         flags=flags, stream=stream.cuda_stream, rebin_every=args.rebin_every, slab=(lo, hi))
+        up = lambda: eng._check(eng.lib.mpm_upload_particles_ids(eng.h, host.data_ptr(), ids.data_ptr(), n_local, 0))
+        up()
+        r = parallel.SlabRank(eng, rank, world, dev)
+        ex = parallel.DistExchange(r)
+        parallel.step_dist(r, ex, args.warm_substeps)
+        if eng.poll_status() != 0:
+            raise SystemExit("rank %d: engine status after warm-up: %s" % (rank, eng.lib.mpm_last_error(eng.h)))
+        parallel.step_dist(r, ex, args.warmup)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+        eng.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dist.barrier()
+        torch.cuda.synchronize()
+        t_wall0 = time.time()
+        e0.record(stream)
+        parallel.step_dist(r, ex, args.steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t_wall1 = time.time()
+        ms_t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)  # device time, max over ranks
+        ms = float(ms_t)
+        prof = eng.profile()
+        eng.profile_enable(False)
+        clocks = sampler.stop(t_wall0, t_wall1)
+        if eng.poll_status() != 0:
+            raise SystemExit("rank %d: engine flagged an error during the timed region" % rank)
+        live = torch.tensor([eng.count], dtype=torch.int64, device=dev)
+        dist.all_reduce(live)
+        assert int(live) == n_total, "particles lost in migration: %d != %d" % (int(live), n_total)
+        value = n_total * args.steps / (ms * 1e-3)
+
+        # ---- e2e: every rank uploads its host buffer, FRAME substeps, reads its particles back -------
+        def e2e_call():
+            up()
+            parallel.step_dist(r, ex, FRAME)
+            got = eng.lib.mpm_read_particles_ids(eng.h, host.data_ptr(), ids_out.data_ptr(), min(n_max, ids_out.numel()), 0)
+            assert got >= 0, eng.lib.mpm_last_error(eng.h)
+        e2e_call()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_calls):
+            e2e_call()
+        torch.cuda.synchronize()
+        dist.barrier()
+        e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+        e2e_value = n_total * FRAME * args.e2e_calls / float(e2e_t)
+        eng.close()
+    if rank == 0:
+        line = make_line(args, world, n_total, n_local, 14, dim, n_grid, alpha, dt, descr, ms, value, e2e_value, prof,
+                         clocks, scaling="weak",
+                         extra_config={"decomposition": "x-slabs, %d columns per GPU" % (hi - lo),
+                                       "weak_scaling_rule": "n_grid = 8192*sqrt(N), same fill fractions: particles "
+                                                            "and nodes per GPU as at N=1",
+                                       "exchange": "NCCL P2P: 2 ghost node columns each way + emigrant records"})
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

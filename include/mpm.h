@@ -117,6 +117,13 @@ int mpm_read_particles(mpm_handle *h, void *aos_out, long long n, int to_device)
  * out = (slab columns) * (n_grid+1)^(dim-1) * (dim+1) floats, [i][j]([k]) row-major like :47. */
 int mpm_read_grid(mpm_handle *h, int stage, float *out);
 
+/* Same as the two calls above with caller-chosen persistent ids (x-slab runs: each handle holds a
+ * subset of a global particle set).  read: records come back in STORAGE order, ids_out[i] = the id of
+ * record i or -1 for a slot whose particle emigrated; buffers must hold mpm_storage_extent() records;
+ * returns the number of records written. */
+int mpm_upload_particles_ids(mpm_handle *h, const void *aos, const int *ids, long long n, int on_device);
+long long mpm_read_particles_ids(mpm_handle *h, void *aos_out, int *ids_out, long long max_n, int to_device);
+long long mpm_storage_extent(const mpm_handle *h);
 long long mpm_particle_count(const mpm_handle *h);
 int mpm_synchronize(mpm_handle *h);
 /* Sticky device-side status (MPM_E_DOMAIN / MPM_E_CFL) accumulated since the last call; synchronises. */
@@ -158,7 +165,16 @@ typedef struct mpm_halo_desc {
   long long bytes;         /* bytes per message */
 } mpm_halo_desc;
 int mpm_halo_describe(mpm_handle *h, mpm_halo_desc *d);
-/* substep, split at its exchange points: P2G | halo sum | grid update + G2P | migration */
+/* One substep of an x-slab, split at its exchange points:
+ *   mpm_step_p2g                       clear + P2G of the owned particles
+ *   [send_hi -> upper.recv_lo, send_lo -> lower.recv_hi]   2 node columns each way
+ *   mpm_step_halo_add(have_lo, have_hi) own partial sums + the neighbour's (commutative: both sides
+ *                                      end with bit-identical shared columns)
+ *   mpm_step_grid_g2p                  grid update (shared columns redundantly) + G2P; particles whose
+ *                                      new base cell left [slab_lo, slab_hi) are packed for migration
+ *   mpm_migration_describe             synchronises; counts + buffers of the emigrants
+ *   [send_hi[0:n_send_hi] -> upper.recv_lo, send_lo[0:n_send_lo] -> lower.recv_hi]
+ *   mpm_step_immigrate(n_lo, n_hi)     appends the immigrants; re-sorts storage when due */
 int mpm_step_p2g(mpm_handle *h, float dt);
 int mpm_step_halo_add(mpm_handle *h, int have_lo, int have_hi);
 int mpm_step_grid_g2p(mpm_handle *h, float dt);
@@ -168,7 +184,7 @@ typedef struct mpm_migration_desc {
   long long n_send_lo, n_send_hi;  /* counts */
   void *recv_lo, *recv_hi;         /* device: landing zones */
   long long recv_capacity;         /* records per landing zone */
-  int record_bytes;                /* 56+8 (2D) or 104+8 (3D): record + 64-bit global id */
+  int record_bytes;                /* 56+8 (2D) or 104+8 (3D): record + int32 id + pad */
 } mpm_migration_desc;
 int mpm_migration_describe(mpm_handle *h, mpm_migration_desc *d);
 int mpm_step_immigrate(mpm_handle *h, long long n_recv_lo, long long n_recv_hi);

@@ -17,7 +17,24 @@
 
 namespace mpm {
 
-enum { STATUS_DOMAIN = 1, STATUS_CFL = 2 };
+enum { STATUS_DOMAIN = 1, STATUS_CFL = 2, STATUS_MIGRATION_OVERFLOW = 4 };
+
+// Material-id value of a storage slot whose particle emigrated to a neighbouring slab; every kernel
+// skips it and the next re-sort drops it.  (c == INT_MIN is therefore reserved at the C-ABI.)
+constexpr int DEAD = (int)0x80000000;
+
+// Emigrant staging of one handle (x-slab runs only): packed records = the AoS record + id + pad.
+struct MigPtrs {
+  float *send_lo, *send_hi;  // device, `cap` records each
+  int *count;                // device: [0] = lo, [1] = hi
+  int cap;
+  int enabled;
+};
+template <int D>
+struct MigRec {
+  static constexpr int AOS = 2 * D + 2 * D * D + 2;  // 14 | 26 words
+  static constexpr int WORDS = AOS + 2;              // + id + pad: 16 | 28 words (64 | 112 B)
+};
 
 template <int D>
 struct SoA;
@@ -118,6 +135,11 @@ __device__ __forceinline__ void store_tags(const SoA<2> &s, long long i, int mat
 __device__ __forceinline__ void store_tags(const SoA<3> &s, long long i, int /*mat: lives in vm.w*/, int id) {
   s.id[i] = id;
 }
+// store_state() that follows writes vm.w = DEAD in 3D (p.mat); 2D keeps mat in its own array
+__device__ __forceinline__ void mark_dead(const SoA<2> &s, long long i) { s.mat[i] = DEAD; }
+__device__ __forceinline__ void mark_dead(const SoA<3> &, long long) {}
+__device__ __forceinline__ int load_mat(const SoA<2> &s, long long i) { return s.mat[i]; }
+__device__ __forceinline__ int load_mat(const SoA<3> &s, long long i) { return __float_as_int(s.vm[i].w); }
 __device__ __forceinline__ void load_pos(const SoA<2> &s, long long i, float *x) {
   float2 v = s.x[i];
   x[0] = v.x; x[1] = v.y;

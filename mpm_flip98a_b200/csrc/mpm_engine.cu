@@ -59,6 +59,19 @@ struct mpm_handle {
   int *cell_dev = nullptr;
   int key_bits = 0;
 
+  // x-slab exchange (multi == this handle owns a strict sub-range of base-cell columns)
+  bool multi = false;
+  MigPtrs mig = {nullptr, nullptr, nullptr, 0, 0};
+  float *mig_recv_lo = nullptr, *mig_recv_hi = nullptr;
+  float4 *halo_recv_lo = nullptr, *halo_recv_hi = nullptr;
+  int *mig_count_host = nullptr;  // pinned, 2 ints
+  long long mig_sent[2] = {0, 0};
+  bool mig_counts_valid = false;
+  long long n_binned = 0;  // storage slots covered by bin_start (slots beyond are immigrants since the last re-sort)
+  long long live = 0;      // particles owned (storage extent n also counts dead slots)
+  long long halo_nodes() const { return 2LL * P.n1 * (D == 3 ? P.n1 : 1); }
+  int mig_words() const { return D == 2 ? MigRec<2>::WORDS : MigRec<3>::WORDS; }
+
   // AoS staging at the ABI
   float *stage = nullptr;
   long long stage_records = 0;
@@ -129,8 +142,12 @@ struct mpm_handle {
   }
 
   int init();
-  int upload(const void *aos, long long count, int on_device);
+  int upload(const void *aos, const int *ids, long long count, int on_device);
   int read(void *aos_out, long long count, int to_device);
+  long long read_ids(void *aos_out, int *ids_out, long long max_n, int to_device);
+  int halo_add(int have_lo, int have_hi);
+  int migration_describe(mpm_migration_desc *d);
+  int immigrate(long long n_lo, long long n_hi);
   int rebin_storage();
   int substep(float dt, int n_steps);
   int step_p2g(float dt);
@@ -154,6 +171,7 @@ struct mpm_handle {
       cudaEventDestroy(sp.b);
     }
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    if (mig_count_host) cudaFreeHost(mig_count_host);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 };
@@ -176,6 +194,7 @@ static int validate(const mpm_config &c, std::string &why) {
     if (c.materials[m].kind < 0 || c.materials[m].kind > 2) BAD("material %d: unknown kind %d", m, c.materials[m].kind);
   if (c.capacity < 1 || c.capacity > 2000000000LL) BAD("capacity must be in [1, 2e9] (got %lld)", c.capacity);
   if (c.slab_lo < 0 || c.slab_hi > c.n_grid || c.slab_lo >= c.slab_hi) BAD("bad slab [%d,%d)", c.slab_lo, c.slab_hi);
+  if ((c.slab_lo > 0 || c.slab_hi < c.n_grid) && c.slab_hi - c.slab_lo < 2) BAD("a slab must own at least 2 columns [%d,%d)", c.slab_lo, c.slab_hi);
   if (c.bin_edge < 0 || c.bin_edge > 64) BAD("bin_edge must be 0..64 (got %d)", c.bin_edge);
   return MPM_OK;
 #undef BAD
@@ -253,13 +272,26 @@ int mpm_handle::init() {
   int edge = cfg.bin_edge > 0 ? cfg.bin_edge : (D == 2 ? 8 : 4);
   G = make_bin_geom(P, D, edge);
   key_bits = 1;
-  while ((1LL << key_bits) < G.n_bins) key_bits++;
+  while ((1LL << key_bits) < (long long)G.n_bins + 1) key_bits++;  // + the bin of dead (emigrated) slots
   sb.capacity = cap;
   for (int b = 0; b < 2; b++)
     if ((rc = dalloc(&sb.key[b], cap)) || (rc = dalloc(&sb.val[b], cap))) return rc;
   if ((rc = dalloc(&sb.hist, sort_hist_elems(cap)))) return rc;
   if ((rc = dalloc(&sb.scan_tmp, scan_tmp_elems((long long)sort_hist_elems(cap))))) return rc;
-  if ((rc = dalloc(&bin_start, (size_t)G.n_bins + 1))) return rc;
+  if ((rc = dalloc(&bin_start, (size_t)G.n_bins + 2))) return rc;
+  multi = cfg.slab_lo > 0 || cfg.slab_hi < cfg.n_grid;
+  if (multi) {
+    mig.cap = (int)(cap / 64 > 4096 ? cap / 64 : 4096);
+    mig.enabled = 1;
+    size_t words = (size_t)mig.cap * mig_words();
+    if ((rc = dalloc(&mig.send_lo, words)) || (rc = dalloc(&mig.send_hi, words)) || (rc = dalloc(&mig_recv_lo, words)) ||
+        (rc = dalloc(&mig_recv_hi, words)) || (rc = dalloc(&mig.count, 4)))
+      return rc;
+    if ((rc = dalloc(&halo_recv_lo, (size_t)halo_nodes())) || (rc = dalloc(&halo_recv_hi, (size_t)halo_nodes()))) return rc;
+    MPM_CUDA(cudaMemsetAsync(mig.count, 0, 16, stream));
+    MPM_CUDA(cudaHostAlloc((void **)&mig_count_host, 16, cudaHostAllocDefault));
+    mig_count_host[0] = mig_count_host[1] = 0;
+  }
   binned = !(cfg.flags & MPM_FLAG_NAIVE) && (D == 2 ? p2g_cells_supported<2>(G) : p2g_cells_supported<3>(G));
 
   stage_records = cap < (1LL << 22) ? cap : (1LL << 22);  // <= 4M records (224 / 416 MB) per chunk
@@ -268,7 +300,7 @@ int mpm_handle::init() {
   return MPM_OK;
 }
 
-int mpm_handle::upload(const void *aos, long long count, int on_device) {
+int mpm_handle::upload(const void *aos, const int *ids, long long count, int on_device) {
   if (count < 0 || (count > 0 && !aos)) {
     err = "upload: bad arguments";
     return MPM_E_INVALID;
@@ -287,13 +319,24 @@ int mpm_handle::upload(const void *aos, long long count, int on_device) {
       MPM_CUDA(cudaMemcpyAsync(stage, src, (size_t)c * W * 4, cudaMemcpyHostToDevice, stream));
       dev_src = stage;
     }
-    if (D == 2) launch_aos_to_soa<2>(dev_src, first, c, s2[cur], stream);
-    else launch_aos_to_soa<3>(dev_src, first, c, s3[cur], stream);
+    const int *dev_ids = nullptr;
+    if (ids) {
+      if (on_device) {
+        dev_ids = ids + first;
+      } else {  // stage the ids behind the records' sort scratch (free during an upload)
+        MPM_CUDA(cudaMemcpyAsync(sb.val[0], ids + first, (size_t)c * 4, cudaMemcpyHostToDevice, stream));
+        dev_ids = sb.val[0];
+      }
+    }
+    if (D == 2) launch_aos_to_soa<2>(dev_src, first, c, s2[cur], dev_ids, stream);
+    else launch_aos_to_soa<3>(dev_src, first, c, s3[cur], dev_ids, stream);
     // the staging buffer is reused by the next chunk; the copy and the kernel are stream-ordered
   }
   MPM_CUDA(cudaGetLastError());
   n = count;
+  live = count;
   tap_valid = false;
+  mig_counts_valid = false;
   int rc = rebin_storage();
   if (rc) return rc;
   MPM_CUDA(cudaStreamSynchronize(stream));  // the caller may free `aos` on return
@@ -309,16 +352,23 @@ int mpm_handle::rebin_storage() {
   else launch_bin_keys<3>(P, G, s3[cur], n, nullptr, sb.key[0], status_dev, false, stream);
   launch_iota(sb.val[0], n, stream);
   int r = radix_sort_pairs(sb, n, key_bits, stream);
-  launch_bin_starts(sb.key[r], n, G.n_bins, bin_start, stream);
+  launch_bin_starts(sb.key[r], n, G.n_bins + 1, bin_start, stream);
   if (D == 2) launch_reorder<2>(s2[cur], s2[cur ^ 1], sb.val[r], n, stream);
   else launch_reorder<3>(s3[cur], s3[cur ^ 1], sb.val[r], n, stream);
   cur ^= 1;
   MPM_CUDA(cudaGetLastError());
+  if (multi) {  // dead (emigrated) slots sorted behind the last bin: drop them from the storage extent
+    int live_extent = 0;
+    MPM_CUDA(cudaMemcpyAsync(&live_extent, bin_start + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
+    MPM_CUDA(cudaStreamSynchronize(stream));
+    n = live_extent;
+  }
+  n_binned = n;
   return MPM_OK;
 }
 
 int mpm_handle::read(void *aos_out, long long count, int to_device) {
-  if (count < 0 || count > n || (count > 0 && !aos_out)) {
+  if (count < 0 || count > live || (count > 0 && !aos_out)) {
     err = "read: bad arguments";
     return MPM_E_INVALID;
   }
@@ -328,8 +378,8 @@ int mpm_handle::read(void *aos_out, long long count, int to_device) {
     long long c = count - first < stage_records ? count - first : stage_records;
     float *dst = (float *)aos_out + first * W;
     float *dev_dst = to_device ? dst : stage;
-    if (D == 2) launch_soa_to_aos<2>(s2[cur], n, first, c, dev_dst, stream);
-    else launch_soa_to_aos<3>(s3[cur], n, first, c, dev_dst, stream);
+    if (D == 2) launch_soa_to_aos<2>(s2[cur], n, first, c, dev_dst, nullptr, stream);
+    else launch_soa_to_aos<3>(s3[cur], n, first, c, dev_dst, nullptr, stream);
     if (!to_device) MPM_CUDA(cudaMemcpyAsync(dst, stage, (size_t)c * W * 4, cudaMemcpyDeviceToHost, stream));
   }
   MPM_CUDA(cudaGetLastError());
@@ -345,11 +395,14 @@ int mpm_handle::step_p2g(float dt) {
   Phase ph(this, MPM_PHASE_P2G, n > 0 ? 1 : 0);
   const bool strict = (cfg.flags & MPM_FLAG_STRICT) != 0;
   if (binned) {
-    if (D == 2) launch_p2g_cells<2>(P, G, dt, s2[cur], n, bin_start, gp<2>(), status_dev, stats_dev, strict, stream);
-    else launch_p2g_cells<3>(P, G, dt, s3[cur], n, bin_start, gp<3>(), status_dev, stats_dev, strict, stream);
+    if (D == 2) launch_p2g_cells<2>(P, G, dt, s2[cur], n_binned, bin_start, gp<2>(), status_dev, stats_dev, strict, stream);
+    else launch_p2g_cells<3>(P, G, dt, s3[cur], n_binned, bin_start, gp<3>(), status_dev, stats_dev, strict, stream);
+    // immigrants since the last re-sort sit behind the binned range: per-particle scatter
+    if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), status_dev, stream);
+    else launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), status_dev, stream);
   } else {
-    if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], n, gp<2>(), status_dev, stream);
-    else launch_p2g_naive<3>(P, dt, s3[cur], n, gp<3>(), status_dev, stream);
+    if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), status_dev, stream);
+    else launch_p2g_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), status_dev, stream);
   }
   return MPM_OK;
 }
@@ -366,8 +419,13 @@ int mpm_handle::step_grid_g2p(float dt) {
   }
   {
     Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
-    if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], n, gp<2>(), stream);
-    else launch_g2p_naive<3>(P, dt, s3[cur], n, gp<3>(), stream);
+    if (multi) MPM_CUDA(cudaMemsetAsync(mig.count, 0, 8, stream));
+    if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], n, gp<2>(), mig, status_dev, stream);
+    else launch_g2p_naive<3>(P, dt, s3[cur], n, gp<3>(), mig, status_dev, stream);
+    if (multi) {
+      MPM_CUDA(cudaMemcpyAsync(mig_count_host, mig.count, 8, cudaMemcpyDeviceToHost, stream));
+      mig_counts_valid = true;
+    }
   }
   if (prof_on) prof.substeps++;
   return MPM_OK;
@@ -379,6 +437,10 @@ int mpm_handle::substep(float dt, int n_steps) {
     return MPM_E_INVALID;
   }
   MPM_CUDA(cudaSetDevice(cfg.device));
+  if (multi) {
+    err = "substep: this handle owns an x-slab; drive it with mpm_step_p2g / halo / grid_g2p / immigrate";
+    return MPM_E_STATE;
+  }
   if (!(dt > 0)) dt = cfg.dt;
   int every = cfg.rebin_every == 0 ? (binned ? 16 : 32) : cfg.rebin_every;
   for (int s = 0; s < n_steps; s++) {
@@ -461,10 +523,102 @@ int mpm_handle::poll_status() {
     err = "a particle left the grid (base cell clamped)";
     return MPM_E_DOMAIN;
   }
+  if (st & STATUS_MIGRATION_OVERFLOW) {
+    err = "more emigrants in one substep than the migration buffers hold";
+    return MPM_E_CAPACITY;
+  }
   if (st & STATUS_CFL) {
     err = "a particle crossed more than one bin in one substep";
     return MPM_E_CFL;
   }
+  return MPM_OK;
+}
+
+long long mpm_handle::read_ids(void *aos_out, int *ids_out, long long max_n, int to_device) {
+  if (max_n < n || !aos_out || !ids_out) {
+    err = "read_ids: buffers must hold mpm_storage_extent() records";
+    return MPM_E_INVALID;
+  }
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  const int W = record_words();
+  for (long long first = 0; first < n; first += stage_records) {
+    long long c = n - first < stage_records ? n - first : stage_records;
+    float *dst = (float *)aos_out + first * W;
+    float *dev_dst = to_device ? dst : stage;
+    int *dev_ids = to_device ? ids_out + first : sb.val[0];
+    if (D == 2) launch_soa_to_aos<2>(s2[cur], n, first, c, dev_dst, dev_ids, stream);
+    else launch_soa_to_aos<3>(s3[cur], n, first, c, dev_dst, dev_ids, stream);
+    if (!to_device) {
+      MPM_CUDA(cudaMemcpyAsync(dst, stage, (size_t)c * W * 4, cudaMemcpyDeviceToHost, stream));
+      MPM_CUDA(cudaMemcpyAsync(ids_out + first, sb.val[0], (size_t)c * 4, cudaMemcpyDeviceToHost, stream));
+      MPM_CUDA(cudaStreamSynchronize(stream));  // staging buffers are reused by the next chunk
+    }
+  }
+  MPM_CUDA(cudaGetLastError());
+  MPM_CUDA(cudaStreamSynchronize(stream));
+  return n;
+}
+
+int mpm_handle::halo_add(int have_lo, int have_hi) {
+  if (!multi) return MPM_OK;
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  Phase ph(this, MPM_PHASE_HALO, (have_lo ? 1 : 0) + (have_hi ? 1 : 0));
+  const long long hn = halo_nodes();
+  if (have_lo) launch_halo_add(grid, halo_recv_lo, hn, stream);
+  if (have_hi) launch_halo_add(grid + (nodes - hn), halo_recv_hi, hn, stream);
+  MPM_CUDA(cudaGetLastError());
+  return MPM_OK;
+}
+
+int mpm_handle::migration_describe(mpm_migration_desc *d) {
+  memset(d, 0, sizeof *d);
+  d->record_bytes = mig_words() * 4;
+  if (!multi) return MPM_OK;
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  MPM_CUDA(cudaStreamSynchronize(stream));
+  if (mig_counts_valid) {  // emigrants of the last G2P leave this handle now
+    for (int k = 0; k < 2; k++) {
+      mig_sent[k] = mig_count_host[k] < mig.cap ? mig_count_host[k] : mig.cap;
+      live -= mig_sent[k];
+    }
+    mig_counts_valid = false;
+  }
+  d->send_lo = mig.send_lo;
+  d->send_hi = mig.send_hi;
+  d->n_send_lo = mig_sent[0];
+  d->n_send_hi = mig_sent[1];
+  d->recv_lo = mig_recv_lo;
+  d->recv_hi = mig_recv_hi;
+  d->recv_capacity = mig.cap;
+  return MPM_OK;
+}
+
+int mpm_handle::immigrate(long long n_lo, long long n_hi) {
+  if (!multi) return MPM_OK;
+  if (n_lo < 0 || n_hi < 0 || n_lo > mig.cap || n_hi > mig.cap) {
+    err = "immigrate: counts exceed the landing zones";
+    return MPM_E_INVALID;
+  }
+  if (n + n_lo + n_hi > cap) {
+    err = "immigrate: storage full (capacity must leave room for immigrants between re-sorts)";
+    return MPM_E_CAPACITY;
+  }
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  Phase ph(this, MPM_PHASE_MIGRATE, (n_lo ? 1 : 0) + (n_hi ? 1 : 0));
+  if (D == 2) {
+    launch_immigrate<2>(mig_recv_lo, n_lo, s2[cur], n, stream);
+    launch_immigrate<2>(mig_recv_hi, n_hi, s2[cur], n + n_lo, stream);
+  } else {
+    launch_immigrate<3>(mig_recv_lo, n_lo, s3[cur], n, stream);
+    launch_immigrate<3>(mig_recv_hi, n_hi, s3[cur], n + n_lo, stream);
+  }
+  n += n_lo + n_hi;
+  live += n_lo + n_hi;
+  mig_sent[0] = mig_sent[1] = 0;
+  steps_since_sort++;
+  int every = cfg.rebin_every == 0 ? (binned ? 16 : 32) : cfg.rebin_every;
+  if (every > 0 && steps_since_sort >= every) return rebin_storage();
+  MPM_CUDA(cudaGetLastError());
   return MPM_OK;
 }
 
@@ -539,14 +693,21 @@ void mpm_destroy(mpm_handle *h) { delete h; }
 const char *mpm_last_error(const mpm_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int mpm_upload_particles(mpm_handle *h, const void *aos, long long n, int on_device) {
-  return h ? h->upload(aos, n, on_device) : MPM_E_INVALID;
+  return h ? h->upload(aos, nullptr, n, on_device) : MPM_E_INVALID;
 }
+int mpm_upload_particles_ids(mpm_handle *h, const void *aos, const int *ids, long long n, int on_device) {
+  return h ? h->upload(aos, ids, n, on_device) : MPM_E_INVALID;
+}
+long long mpm_read_particles_ids(mpm_handle *h, void *aos_out, int *ids_out, long long max_n, int to_device) {
+  return h ? h->read_ids(aos_out, ids_out, max_n, to_device) : MPM_E_INVALID;
+}
+long long mpm_storage_extent(const mpm_handle *h) { return h ? h->n : -1; }
 int mpm_substep(mpm_handle *h, float dt, int n_steps) { return h ? h->substep(dt, n_steps) : MPM_E_INVALID; }
 int mpm_read_particles(mpm_handle *h, void *aos_out, long long n, int to_device) {
   return h ? h->read(aos_out, n, to_device) : MPM_E_INVALID;
 }
 int mpm_read_grid(mpm_handle *h, int stage, float *out) { return h ? h->read_grid(stage, out) : MPM_E_INVALID; }
-long long mpm_particle_count(const mpm_handle *h) { return h ? h->n : -1; }
+long long mpm_particle_count(const mpm_handle *h) { return h ? h->live : -1; }
 int mpm_synchronize(mpm_handle *h) {
   if (!h) return MPM_E_INVALID;
   cudaSetDevice(h->cfg.device);
@@ -590,32 +751,33 @@ int mpm_bin_particles(mpm_handle *h, int *cell, int *key, int *order, int *bin_s
 // ---- x-slab phases -------------------------------------------------------------------------------
 int mpm_halo_describe(mpm_handle *h, mpm_halo_desc *d) {
   if (!h || !d) return MPM_E_INVALID;
-  h->err = "halo exchange: not built yet";
-  return MPM_E_STATE;
+  memset(d, 0, sizeof *d);
+  if (!h->multi) return MPM_OK;
+  const long long hn = h->halo_nodes();
+  d->send_lo = h->grid;
+  d->send_hi = h->grid + (h->nodes - hn);
+  d->recv_lo = h->halo_recv_lo;
+  d->recv_hi = h->halo_recv_hi;
+  d->bytes = hn * (long long)sizeof(float4);
+  return MPM_OK;
 }
 int mpm_step_p2g(mpm_handle *h, float dt) {
   if (!h) return MPM_E_INVALID;
+  cudaSetDevice(h->cfg.device);
   if (!(dt > 0)) dt = h->cfg.dt;
   return h->step_p2g(dt);
 }
-int mpm_step_halo_add(mpm_handle *h, int, int) {
-  if (!h) return MPM_E_INVALID;
-  h->err = "halo exchange: not built yet";
-  return MPM_E_STATE;
-}
+int mpm_step_halo_add(mpm_handle *h, int have_lo, int have_hi) { return h ? h->halo_add(have_lo, have_hi) : MPM_E_INVALID; }
 int mpm_step_grid_g2p(mpm_handle *h, float dt) {
   if (!h) return MPM_E_INVALID;
+  cudaSetDevice(h->cfg.device);
   if (!(dt > 0)) dt = h->cfg.dt;
   return h->step_grid_g2p(dt);
 }
 int mpm_migration_describe(mpm_handle *h, mpm_migration_desc *d) {
-  if (!h || !d) return MPM_E_INVALID;
-  h->err = "migration: not built yet";
-  return MPM_E_STATE;
+  return (h && d) ? h->migration_describe(d) : MPM_E_INVALID;
 }
-int mpm_step_immigrate(mpm_handle *h, long long, long long) {
-  if (!h) return MPM_E_INVALID;
-  h->err = "migration: not built yet";
-  return MPM_E_STATE;
+int mpm_step_immigrate(mpm_handle *h, long long n_lo, long long n_hi) {
+  return h ? h->immigrate(n_lo, n_hi) : MPM_E_INVALID;
 }
 }

@@ -50,12 +50,13 @@ template void launch_grid_update<3>(const Params &, float, GridPtrs<3>, cudaStre
 // naive P2G: one thread per particle, 3^D vector REDs (RED.E.ADD.F32x4) into L2.
 // ------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void __launch_bounds__(128) k_p2g_naive(Params P, float dt, SoA<D> s, long long n, float4 *__restrict__ grid,
-                                                   int *__restrict__ status) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128) k_p2g_naive(Params P, float dt, SoA<D> s, long long first, long long n,
+                                                   float4 *__restrict__ grid, int *__restrict__ status) {
+  long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   PState<D> p;
   load_full(s, i, p);
+  if (p.mat == DEAD) return;
   Stencil<D> st = make_stencil<D>(p.x, P.inv_dx);
   int bad = clamp_base<D>(P, st.base);
   if (bad) atomicOr(status, bad);
@@ -79,14 +80,16 @@ __global__ void __launch_bounds__(128) k_p2g_naive(Params P, float dt, SoA<D> s,
 }
 
 template <int D>
-void launch_p2g_naive(const Params &P, float dt, const SoA<D> &s, long long n, GridPtrs<D> g, int *status,
-                      cudaStream_t st) {
-  if (n <= 0) return;
-  unsigned blocks = (unsigned)((n + 127) / 128);
-  k_p2g_naive<D><<<blocks, 128, 0, st>>>(P, dt, s, n, g.g, status);
+void launch_p2g_naive(const Params &P, float dt, const SoA<D> &s, long long first, long long n, GridPtrs<D> g,
+                      int *status, cudaStream_t st) {
+  if (n - first <= 0) return;
+  unsigned blocks = (unsigned)((n - first + 127) / 128);
+  k_p2g_naive<D><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, status);
 }
-template void launch_p2g_naive<2>(const Params &, float, const SoA<2> &, long long, GridPtrs<2>, int *, cudaStream_t);
-template void launch_p2g_naive<3>(const Params &, float, const SoA<3> &, long long, GridPtrs<3>, int *, cudaStream_t);
+template void launch_p2g_naive<2>(const Params &, float, const SoA<2> &, long long, long long, GridPtrs<2>, int *,
+                                  cudaStream_t);
+template void launch_p2g_naive<3>(const Params &, float, const SoA<3> &, long long, long long, GridPtrs<3>, int *,
+                                  cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
 // binned P2G ("cell gather"): one CTA per bin of B^D cells.  No floating-point atomics in shared
@@ -170,7 +173,7 @@ __global__ void __launch_bounds__(NT, MPM_P2G_MINB) k_p2g_cells(Params P, BinGeo
   const int tid = threadIdx.x;
   const int bin = blockIdx.x;
   const int s0 = bin_start[bin], s1 = bin_start[bin + 1];
-  if (s0 == s1) return;
+  if (s0 >= s1) return;
   // bin coordinates -> origin (global cell index of local cell 0, i.e. bin origin minus the margin)
   int o[3] = {0, 0, 0};
   {
@@ -188,6 +191,10 @@ __global__ void __launch_bounds__(NT, MPM_P2G_MINB) k_p2g_cells(Params P, BinGeo
     for (int i = tid; i < m; i += NT) {
       PState<D> p;
       load_full(s, (long long)c0 + i, p);
+      if (p.mat == DEAD) {  // emigrated to a neighbouring slab since the last re-sort
+        cell_of[i] = 0xffffu;
+        continue;
+      }
       Stencil<D> st = make_stencil<D>(p.x, P.inv_dx);
       int bad = clamp_base<D>(P, st.base);
       if (bad) atomicOr(status, bad);
@@ -415,12 +422,14 @@ template void launch_p2g_cells<3>(const Params &, const BinGeom &, float, const 
 // ------------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(128) k_g2p_naive(Params P, float dt, SoA<D> s, long long n,
-                                                   const float4 *__restrict__ grid, const void *__restrict__ vold_) {
+                                                   const float4 *__restrict__ grid, const void *__restrict__ vold_,
+                                                   MigPtrs mig, int *__restrict__ status) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const bool flip = P.alpha != 0.0f;
   PState<D> p;
   load_g2p(s, i, p, flip);
+  if (p.mat == DEAD) return;
   Stencil<D> st = make_stencil<D>(p.x, P.inv_dx);
   clamp_base<D>(P, st.base);
   const Material &mat = P.mat[material_index(P, p.mat)];
@@ -457,23 +466,111 @@ __global__ void __launch_bounds__(128) k_g2p_naive(Params P, float dt, SoA<D> s,
   for (int c = 0; c < D; c++) p.v[c] = v[c];
   p.C = C;
   g2p_finish<D>(P, mat, dt, p.x, p.v, p.C, p.F, p.Jp, v_in, dv);
+  if (mig.enabled) {
+    // x-slab ownership follows the base cell of the NEW position (what the next P2G will use, :55)
+    int bx = base_coord(p.x[0], P.inv_dx);
+    bx = max(0, min(bx, P.n_grid - 2));
+    const int side = bx < P.slab_lo ? 0 : (bx >= P.slab_hi ? 1 : -1);
+    if (side >= 0) {
+      int slot = atomicAdd(&mig.count[side], 1);
+      if (slot < mig.cap) {
+        constexpr int W = MigRec<D>::WORDS;
+        float *r = (side == 0 ? mig.send_lo : mig.send_hi) + (size_t)slot * W;
+        float rec[W];
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+          rec[c] = p.x[c];
+          rec[D + c] = p.v[c];
+        }
+#pragma unroll
+        for (int c = 0; c < D; c++)
+#pragma unroll
+          for (int k = 0; k < D; k++) {
+            rec[2 * D + c * D + k] = p.F.d[c][k];
+            rec[2 * D + D * D + c * D + k] = p.C.d[c][k];
+          }
+        rec[2 * D + 2 * D * D] = p.Jp;
+        rec[2 * D + 2 * D * D + 1] = __int_as_float(p.mat);
+        rec[W - 2] = __int_as_float(s.id[i]);
+        rec[W - 1] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < W / 4; k++)
+          reinterpret_cast<float4 *>(r)[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+        p.mat = DEAD;
+        mark_dead(s, i);
+      } else {
+        atomicOr(status, STATUS_MIGRATION_OVERFLOW);  // stays here (and will be flagged out of slab)
+      }
+    }
+  }
   store_state(s, i, p);
 }
 
 template <int D>
-void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long n, GridPtrs<D> g, cudaStream_t st) {
+void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long n, GridPtrs<D> g, MigPtrs mig, int *status,
+                      cudaStream_t st) {
   if (n <= 0) return;
   unsigned blocks = (unsigned)((n + 127) / 128);
-  k_g2p_naive<D><<<blocks, 128, 0, st>>>(P, dt, s, n, g.g, g.vold);
+  k_g2p_naive<D><<<blocks, 128, 0, st>>>(P, dt, s, n, g.g, g.vold, mig, status);
 }
-template void launch_g2p_naive<2>(const Params &, float, const SoA<2> &, long long, GridPtrs<2>, cudaStream_t);
-template void launch_g2p_naive<3>(const Params &, float, const SoA<3> &, long long, GridPtrs<3>, cudaStream_t);
+template void launch_g2p_naive<2>(const Params &, float, const SoA<2> &, long long, GridPtrs<2>, MigPtrs, int *,
+                                  cudaStream_t);
+template void launch_g2p_naive<3>(const Params &, float, const SoA<3> &, long long, GridPtrs<3>, MigPtrs, int *,
+                                  cudaStream_t);
+
+// ------------------------------------------------------------------------------------------------
+// x-slab exchange helpers: ghost-column sum, immigrant unpack
+// ------------------------------------------------------------------------------------------------
+__global__ void k_halo_add(float4 *__restrict__ dst, const float4 *__restrict__ src, long long count) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float4 a = dst[i], b = src[i];
+  // own partial + neighbour's partial: the neighbour computes b + a, the same float (commutative)
+  dst[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+void launch_halo_add(float4 *dst, const float4 *src, long long count, cudaStream_t st) {
+  if (count <= 0) return;
+  k_halo_add<<<(unsigned)((count + 255) / 256), 256, 0, st>>>(dst, src, count);
+}
+
+template <int D>
+__global__ void k_immigrate(const float *__restrict__ recv, long long count, SoA<D> s, long long first) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= count) return;
+  constexpr int W = MigRec<D>::WORDS;
+  const float *r = recv + t * W;
+  PState<D> p;
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    p.x[c] = r[c];
+    p.v[c] = r[D + c];
+  }
+#pragma unroll
+  for (int c = 0; c < D; c++)
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+      p.F.d[c][k] = r[2 * D + c * D + k];
+      p.C.d[c][k] = r[2 * D + D * D + c * D + k];
+    }
+  p.Jp = r[2 * D + 2 * D * D];
+  p.mat = __float_as_int(r[2 * D + 2 * D * D + 1]);
+  store_state(s, first + t, p);
+  store_tags(s, first + t, p.mat, __float_as_int(r[W - 2]));
+}
+template <int D>
+void launch_immigrate(const float *recv, long long count, const SoA<D> &s, long long first, cudaStream_t st) {
+  if (count <= 0) return;
+  k_immigrate<D><<<(unsigned)((count + 255) / 256), 256, 0, st>>>(recv, count, s, first);
+}
+template void launch_immigrate<2>(const float *, long long, const SoA<2> &, long long, cudaStream_t);
+template void launch_immigrate<3>(const float *, long long, const SoA<3> &, long long, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
 // AoS (the reference's Particle record, :28-42: x v F C Jp c) <-> SoA
 // ------------------------------------------------------------------------------------------------
 template <int D>
-__global__ void k_aos_to_soa(const float *__restrict__ aos, long long first, long long count, SoA<D> s) {
+__global__ void k_aos_to_soa(const float *__restrict__ aos, long long first, long long count, SoA<D> s,
+                             const int *__restrict__ ids) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= count) return;
   constexpr int W = 2 * D + 2 * D * D + 2;
@@ -495,25 +592,33 @@ __global__ void k_aos_to_soa(const float *__restrict__ aos, long long first, lon
   p.mat = __float_as_int(r[2 * D + 2 * D * D + 1]);
   long long i = first + t;
   store_state(s, i, p);
-  store_tags(s, i, p.mat, (int)i);
+  store_tags(s, i, p.mat, ids ? ids[t] : (int)i);
 }
 template <int D>
-void launch_aos_to_soa(const float *aos, long long first, long long count, const SoA<D> &s, cudaStream_t st) {
+void launch_aos_to_soa(const float *aos, long long first, long long count, const SoA<D> &s, const int *ids,
+                       cudaStream_t st) {
   if (count <= 0) return;
-  k_aos_to_soa<D><<<(unsigned)((count + 255) / 256), 256, 0, st>>>(aos, first, count, s);
+  k_aos_to_soa<D><<<(unsigned)((count + 255) / 256), 256, 0, st>>>(aos, first, count, s, ids);
 }
-template void launch_aos_to_soa<2>(const float *, long long, long long, const SoA<2> &, cudaStream_t);
-template void launch_aos_to_soa<3>(const float *, long long, long long, const SoA<3> &, cudaStream_t);
+template void launch_aos_to_soa<2>(const float *, long long, long long, const SoA<2> &, const int *, cudaStream_t);
+template void launch_aos_to_soa<3>(const float *, long long, long long, const SoA<3> &, const int *, cudaStream_t);
 
 template <int D>
-__global__ void k_soa_to_aos(SoA<D> s, long long n, long long id0, long long count, float *__restrict__ aos) {
+__global__ void k_soa_to_aos(SoA<D> s, long long n, long long id0, long long count, float *__restrict__ aos,
+                             int *__restrict__ ids_out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  long long id = s.id[i];
-  if (id < id0 || id >= id0 + count) return;
   constexpr int W = 2 * D + 2 * D * D + 2;
   PState<D> p;
   load_full(s, i, p);
+  long long id = s.id[i];
+  if (ids_out) {  // storage order: records [id0, id0+count) of the storage with their ids (-1 = dead slot)
+    if (i < id0 || i >= id0 + count) return;
+    ids_out[i - id0] = p.mat == DEAD ? -1 : (int)id;
+    id = i;
+  } else if (p.mat == DEAD || id < id0 || id >= id0 + count) {
+    return;
+  }
   float *r = aos + (id - id0) * W;
 #pragma unroll
   for (int c = 0; c < D; c++) {
@@ -531,12 +636,13 @@ __global__ void k_soa_to_aos(SoA<D> s, long long n, long long id0, long long cou
   r[2 * D + 2 * D * D + 1] = __int_as_float(p.mat);
 }
 template <int D>
-void launch_soa_to_aos(const SoA<D> &s, long long n, long long id0, long long count, float *aos, cudaStream_t st) {
+void launch_soa_to_aos(const SoA<D> &s, long long n, long long id0, long long count, float *aos, int *ids_out,
+                       cudaStream_t st) {
   if (n <= 0) return;
-  k_soa_to_aos<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, n, id0, count, aos);
+  k_soa_to_aos<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(s, n, id0, count, aos, ids_out);
 }
-template void launch_soa_to_aos<2>(const SoA<2> &, long long, long long, long long, float *, cudaStream_t);
-template void launch_soa_to_aos<3>(const SoA<3> &, long long, long long, long long, float *, cudaStream_t);
+template void launch_soa_to_aos<2>(const SoA<2> &, long long, long long, long long, float *, int *, cudaStream_t);
+template void launch_soa_to_aos<3>(const SoA<3> &, long long, long long, long long, float *, int *, cudaStream_t);
 
 template <int D>
 __global__ void k_reorder(SoA<D> src, SoA<D> dst, const int *__restrict__ order, long long n) {

@@ -19,10 +19,15 @@ struct GridPtrs {
 
 // ---- naive path: one thread per particle, vector REDs straight into L2 -------------------------
 template <int D>
-void launch_p2g_naive(const Params &P, float dt, const SoA<D> &s, long long n, GridPtrs<D> g, int *status,
-                      cudaStream_t st);
+void launch_p2g_naive(const Params &P, float dt, const SoA<D> &s, long long first, long long n, GridPtrs<D> g,
+                      int *status, cudaStream_t st);
 template <int D>
-void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long n, GridPtrs<D> g, cudaStream_t st);
+void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long n, GridPtrs<D> g, MigPtrs mig, int *status,
+                      cudaStream_t st);
+// x-slab exchange helpers
+void launch_halo_add(float4 *dst, const float4 *src, long long count, cudaStream_t st);
+template <int D>
+void launch_immigrate(const float *recv, long long count, const SoA<D> &s, long long first, cudaStream_t st);
 template <int D>
 void launch_grid_update(const Params &P, float dt, GridPtrs<D> g, cudaStream_t st);
 
@@ -36,10 +41,13 @@ void launch_p2g_cells(const Params &P, const BinGeom &G, float dt, const SoA<D> 
 // ---- AoS <-> SoA at the C-ABI ------------------------------------------------------------------
 // records [first, first+count) of the caller's AoS -> SoA slots [first, first+count), id = index
 template <int D>
-void launch_aos_to_soa(const float *aos, long long first, long long count, const SoA<D> &s, cudaStream_t st);
-// every particle whose id lies in [id0, id0+count) writes its record to aos[(id - id0)]
+void launch_aos_to_soa(const float *aos, long long first, long long count, const SoA<D> &s, const int *ids,
+                       cudaStream_t st);
+// ids_out == NULL: every live particle whose id lies in [id0, id0+count) writes its record to aos[id - id0];
+// ids_out != NULL: storage slots [id0, id0+count) are written in storage order with their ids (-1 = dead)
 template <int D>
-void launch_soa_to_aos(const SoA<D> &s, long long n, long long id0, long long count, float *aos, cudaStream_t st);
+void launch_soa_to_aos(const SoA<D> &s, long long n, long long id0, long long count, float *aos, int *ids_out,
+                       cudaStream_t st);
 // dst[slot] = src[order[slot]] for all fields
 template <int D>
 void launch_reorder(const SoA<D> &src, const SoA<D> &dst, const int *order, long long n, cudaStream_t st);

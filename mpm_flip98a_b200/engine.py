@@ -74,6 +74,9 @@ SYMBOLS = {
     "mpm_substep": (ctypes.c_int, [_H, ctypes.c_float, ctypes.c_int]),
     "mpm_read_particles": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int]),
     "mpm_read_grid": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_void_p]),
+    "mpm_upload_particles_ids": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int]),
+    "mpm_read_particles_ids": (ctypes.c_longlong, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int]),
+    "mpm_storage_extent": (ctypes.c_longlong, [_H]),
     "mpm_particle_count": (ctypes.c_longlong, [_H]),
     "mpm_synchronize": (ctypes.c_int, [_H]),
     "mpm_poll_status": (ctypes.c_int, [_H]),
@@ -186,6 +189,43 @@ class Engine:
         p = np.ascontiguousarray(particles, np.float32)
         assert p.ndim == 2 and p.shape[1] == self.words, "records must be (n, %d) float32" % self.words
         self._check(self.lib.mpm_upload_particles(self.h, p.ctypes.data, p.shape[0], 0))
+
+    def upload_ids(self, particles, ids):
+        p = np.ascontiguousarray(particles, np.float32)
+        ids = np.ascontiguousarray(ids, np.int32)
+        assert p.ndim == 2 and p.shape[1] == self.words and len(ids) == len(p)
+        self._check(self.lib.mpm_upload_particles_ids(self.h, p.ctypes.data, ids.ctypes.data, p.shape[0], 0))
+
+    def read_ids(self):
+        """(records, ids) of the live particles of this handle, storage order."""
+        ext = self.lib.mpm_storage_extent(self.h)
+        out = np.empty((ext, self.words), np.float32)
+        ids = np.empty(ext, np.int32)
+        got = self._check(self.lib.mpm_read_particles_ids(self.h, out.ctypes.data, ids.ctypes.data, ext, 0))
+        keep = ids[:got] >= 0
+        return out[:got][keep], ids[:got][keep]
+
+    def halo(self):
+        d = HaloDesc()
+        self._check(self.lib.mpm_halo_describe(self.h, ctypes.byref(d)))
+        return d
+
+    def migration(self):
+        d = MigrationDesc()
+        self._check(self.lib.mpm_migration_describe(self.h, ctypes.byref(d)))
+        return d
+
+    def step_p2g(self, dt=0.0):
+        self._check(self.lib.mpm_step_p2g(self.h, dt))
+
+    def step_halo_add(self, have_lo, have_hi):
+        self._check(self.lib.mpm_step_halo_add(self.h, int(have_lo), int(have_hi)))
+
+    def step_grid_g2p(self, dt=0.0):
+        self._check(self.lib.mpm_step_grid_g2p(self.h, dt))
+
+    def step_immigrate(self, n_lo, n_hi):
+        self._check(self.lib.mpm_step_immigrate(self.h, n_lo, n_hi))
 
     def upload_device(self, dev_ptr, n):
         self._check(self.lib.mpm_upload_particles(self.h, dev_ptr, n, 1))

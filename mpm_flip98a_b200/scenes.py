@@ -66,16 +66,53 @@ def dam_break_2d(n_grid=2048, per_side=3, seed=2, width=0.45, height=0.90, mat=F
     return make_records(x, mat, 2)
 
 
-def slab_fill_2d(n_grid=8192, per_side=3, seed=3, x_range=(0.05, 0.95), y_range=(0.05, 0.50), bands=True):
-    """BASELINE config 4: a wide pool, three material bands along x."""
-    rng = np.random.RandomState(seed)
-    x = _jittered_box((x_range[0], y_range[0]), (x_range[1], y_range[1]), n_grid, per_side, rng, 2)
-    if bands:
-        t = (x[:, 0] - x_range[0]) / (x_range[1] - x_range[0])
-        mat = np.minimum((t * 3).astype(np.int32), 2)
-    else:
-        mat = FLUID
-    return make_records(x, mat, 2)
+def slab_fill_2d(n_grid=8192, per_side=3, seed=3, x_range=(0.05, 0.95), y_range=(0.05, 0.50), bands=True,
+                 columns=None, out=None, strip=256):
+    """BASELINE config 4: a wide pool, three material bands along x.
+
+    `columns=(c_lo, c_hi)` restricts generation to the cell columns of one x-slab (each column strip has
+    its own seeded stream, so any partition yields the same global scene); `out` (an (n,14) float32
+    array, e.g. pinned memory) is filled strip by strip so no second full-size temporary exists.
+    Returns the records (a view of `out` when given)."""
+    c0 = int(np.ceil(x_range[0] * n_grid - 1e-9))
+    c1 = int(np.floor(x_range[1] * n_grid + 1e-9))
+    if columns is not None:
+        c0, c1 = max(c0, columns[0]), min(c1, columns[1])
+    r0 = int(np.ceil(y_range[0] * n_grid - 1e-9))
+    r1 = int(np.floor(y_range[1] * n_grid + 1e-9))
+    n = max(0, c1 - c0) * (r1 - r0) * per_side * per_side
+    if out is None:
+        out = np.empty((n, 14), np.float32)
+    assert out.shape[0] >= n and out.shape[1] == 14
+    pos = 0
+    for s0 in range((c0 // strip) * strip, c1, strip):
+        a, b = max(s0, c0), min(s0 + strip, c1)
+        if a >= b:
+            continue
+        rng = np.random.RandomState((seed * 1000003 + s0) % (2 ** 31))
+        full = _jittered_box((s0 / n_grid, y_range[0]), ((s0 + strip) / n_grid, y_range[1]), n_grid, per_side, rng, 2)
+        keep = (full[:, 0] >= np.float32(a / n_grid)) & (full[:, 0] < np.float32(b / n_grid)) if (a, b) != (s0, s0 + strip) \
+            else slice(None)
+        x = full[keep]
+        if bands:
+            t = (x[:, 0] - x_range[0]) / (x_range[1] - x_range[0])
+            mat = np.clip((t * 3).astype(np.int32), 0, 2)
+        else:
+            mat = FLUID
+        out[pos:pos + len(x)] = make_records(x, mat, 2)
+        pos += len(x)
+    return out[:pos]
+
+
+def slab_fill_2d_count(n_grid, per_side=3, x_range=(0.05, 0.95), y_range=(0.05, 0.50), columns=None):
+    """Upper bound of the number of particles slab_fill_2d generates (for sizing buffers)."""
+    c0 = int(np.ceil(x_range[0] * n_grid - 1e-9))
+    c1 = int(np.floor(x_range[1] * n_grid + 1e-9))
+    if columns is not None:
+        c0, c1 = max(c0, columns[0]), min(c1, columns[1])
+    r0 = int(np.ceil(y_range[0] * n_grid - 1e-9))
+    r1 = int(np.floor(y_range[1] * n_grid + 1e-9))
+    return max(0, c1 - c0) * (r1 - r0) * per_side * per_side
 
 
 def collapse_3d(n_grid=256, per_side=2, seed=4, y_top=0.35, xz=(0.05, 0.95)):
