@@ -183,9 +183,6 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus, "launch with torchrun --nproc-per-node == --gpus"
     if world > 1:
-        raise SystemExit("multi-GPU slab path not built yet")
-
-    if world > 1:
         return run_slabs(args, rank, world, local)
 
     descr, dim, n_grid, alpha = WORKLOADS[args.workload]
@@ -300,7 +297,7 @@ def make_line(args, world, n_total, n_local, words, dim, n_grid, alpha, dt, desc
                     "d2h_bytes_per_step": n_total * words * 4, "substeps_per_step": FRAME,
                     "call": "mpm_upload_particles + %d substeps + mpm_read_particles, pinned host buffers" % FRAME},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
-            "fallback_particles": prof.get("fallback_particles", 0)}
+            "fallback_particles": prof.get("fallback_particles", 0), "rebin_interval": prof.get("rebin_interval", 0)}
 
 
 def run_slabs(args, rank, world, local):

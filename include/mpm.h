@@ -81,8 +81,9 @@ typedef struct mpm_config {
   int slab_lo, slab_hi;
   void *stream;       /* cudaStream_t to launch on; NULL = a stream owned by the handle */
   int bin_edge;       /* cells per bin edge for the block binning; 0 = engine default */
-  int rebin_every;    /* naive path only: re-sort the particle storage every this many substeps
-                         (0 = engine default, <0 = never); the binned path re-bins every substep */
+  int rebin_every;    /* re-sort the particle storage by bin every this many substeps; <0 = never;
+                         0 = engine default: 32 on the naive path, adaptive 4..128 on the binned path
+                         (doubled while < 0.1% of particle-steps outrun the 1-cell bin margin) */
   int reserved[6];
 } mpm_config;
 
@@ -146,6 +147,7 @@ typedef struct mpm_profile {
   long long substeps;
   long long fallback_particles; /* binned P2G: particles that had drifted past the bin margin and
                                    took the per-particle scatter instead (correct, just slower) */
+  long long rebin_interval;     /* substeps between storage re-sorts right now */
 } mpm_profile;
 int mpm_profile_enable(mpm_handle *h, int on); /* (re)starts accumulation from zero */
 int mpm_profile_read(mpm_handle *h, mpm_profile *out); /* synchronises */

@@ -48,7 +48,18 @@ struct mpm_handle {
   bool tap_valid = false;
 
   int *status_dev = nullptr;
-  unsigned long long *stats_dev = nullptr;  // [0] = binned-P2G fallback particles
+  unsigned long long *stats_dev = nullptr;  // [0] = binned-P2G fallback particles (total), [1] = since the last re-sort
+  // adaptive re-sort interval (binned path, cfg.rebin_every == 0): doubled while almost no particle
+  // outruns the 1-cell bin margin between re-sorts, halved when more than 1% do
+  int rebin_interval = 16;
+  unsigned long long *stats_host = nullptr;  // pinned copy of stats_dev taken at each re-sort
+  cudaEvent_t stats_ev = nullptr;
+  bool stats_pending = false;
+  long long stats_particle_steps = 0;
+  int current_interval() const {
+    if (cfg.rebin_every != 0) return cfg.rebin_every;
+    return binned ? rebin_interval : 32;
+  }
   bool binned = false;                      // CTA-per-bin P2G (default) vs MPM_FLAG_NAIVE
   int status_host_sticky = 0;
 
@@ -172,6 +183,8 @@ struct mpm_handle {
     }
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (mig_count_host) cudaFreeHost(mig_count_host);
+    if (stats_host) cudaFreeHost(stats_host);
+    if (stats_ev) cudaEventDestroy(stats_ev);
     if (own_stream && stream) cudaStreamDestroy(stream);
   }
 };
@@ -238,6 +251,8 @@ int mpm_handle::init() {
   P.slab_hi = cfg.slab_hi;
   int xhi = cfg.slab_hi < cfg.n_grid - 1 ? cfg.slab_hi : cfg.n_grid - 1;  // one past the last owned base column
   P.ncol = xhi - cfg.slab_lo + 2;
+  multi = cfg.slab_lo > 0 || cfg.slab_hi < cfg.n_grid;
+  P.multi = multi ? 1 : 0;
   cap = cfg.capacity;
 
   nodes = (long long)P.ncol * P.n1 * (D == 3 ? P.n1 : 1);
@@ -254,6 +269,8 @@ int mpm_handle::init() {
   MPM_CUDA(cudaMemsetAsync(status_dev, 0, 16, stream));
   if ((rc = dalloc(&stats_dev, 4))) return rc;
   MPM_CUDA(cudaMemsetAsync(stats_dev, 0, 32, stream));
+  MPM_CUDA(cudaHostAlloc((void **)&stats_host, 32, cudaHostAllocDefault));
+  MPM_CUDA(cudaEventCreateWithFlags(&stats_ev, cudaEventDisableTiming));
 
   for (int b = 0; b < 2; b++) {
     if (D == 2) {
@@ -272,14 +289,13 @@ int mpm_handle::init() {
   int edge = cfg.bin_edge > 0 ? cfg.bin_edge : (D == 2 ? 8 : 4);
   G = make_bin_geom(P, D, edge);
   key_bits = 1;
-  while ((1LL << key_bits) < (long long)G.n_bins + 1) key_bits++;  // + the bin of dead (emigrated) slots
+  while ((1LL << key_bits) < (long long)G.n_bins + (multi ? 1 : 0)) key_bits++;  // slabs: + the bin of dead slots
   sb.capacity = cap;
   for (int b = 0; b < 2; b++)
     if ((rc = dalloc(&sb.key[b], cap)) || (rc = dalloc(&sb.val[b], cap))) return rc;
   if ((rc = dalloc(&sb.hist, sort_hist_elems(cap)))) return rc;
   if ((rc = dalloc(&sb.scan_tmp, scan_tmp_elems((long long)sort_hist_elems(cap))))) return rc;
   if ((rc = dalloc(&bin_start, (size_t)G.n_bins + 2))) return rc;
-  multi = cfg.slab_lo > 0 || cfg.slab_hi < cfg.n_grid;
   if (multi) {
     mig.cap = (int)(cap / 64 > 4096 ? cap / 64 : 4096);
     mig.enabled = 1;
@@ -345,6 +361,22 @@ int mpm_handle::upload(const void *aos, const int *ids, long long count, int on_
 
 // keys -> stable sort -> physical reorder into the other SoA buffer; bin_start refreshed
 int mpm_handle::rebin_storage() {
+  if (binned && cfg.rebin_every == 0) {
+    // how many particle-steps of the interval that just ended took the fallback path?
+    if (stats_pending && cudaEventQuery(stats_ev) == cudaSuccess) {
+      const double frac = stats_particle_steps > 0 ? (double)stats_host[1] / (double)stats_particle_steps : 0.0;
+      if (frac < 1e-3 && rebin_interval < 128) rebin_interval *= 2;
+      else if (frac > 1e-2 && rebin_interval > 4) rebin_interval /= 2;
+      stats_pending = false;
+    }
+    if (!stats_pending && steps_since_sort > 0) {
+      MPM_CUDA(cudaMemcpyAsync(stats_host, stats_dev, 32, cudaMemcpyDeviceToHost, stream));
+      MPM_CUDA(cudaEventRecord(stats_ev, stream));
+      MPM_CUDA(cudaMemsetAsync(stats_dev + 1, 0, 8, stream));
+      stats_particle_steps = live * steps_since_sort;
+      stats_pending = true;
+    }
+  }
   steps_since_sort = 0;
   if (n == 0) return MPM_OK;
   Phase ph(this, MPM_PHASE_BIN, 4 + 3 * ((key_bits + 7) / 8));
@@ -442,9 +474,9 @@ int mpm_handle::substep(float dt, int n_steps) {
     return MPM_E_STATE;
   }
   if (!(dt > 0)) dt = cfg.dt;
-  int every = cfg.rebin_every == 0 ? (binned ? 16 : 32) : cfg.rebin_every;
   for (int s = 0; s < n_steps; s++) {
     int rc;
+    const int every = current_interval();
     if (every > 0 && steps_since_sort >= every)
       if ((rc = rebin_storage())) return rc;
     if ((rc = step_p2g(dt))) return rc;
@@ -616,7 +648,7 @@ int mpm_handle::immigrate(long long n_lo, long long n_hi) {
   live += n_lo + n_hi;
   mig_sent[0] = mig_sent[1] = 0;
   steps_since_sort++;
-  int every = cfg.rebin_every == 0 ? (binned ? 16 : 32) : cfg.rebin_every;
+  const int every = current_interval();
   if (every > 0 && steps_since_sort >= every) return rebin_storage();
   MPM_CUDA(cudaGetLastError());
   return MPM_OK;
@@ -741,6 +773,7 @@ int mpm_profile_read(mpm_handle *h, mpm_profile *out) {
   unsigned long long st[4] = {0, 0, 0, 0};
   cudaMemcpy(st, h->stats_dev, sizeof st, cudaMemcpyDeviceToHost);
   h->prof.fallback_particles = (long long)st[0];
+  h->prof.rebin_interval = h->current_interval();
   *out = h->prof;
   return MPM_OK;
 }

@@ -49,14 +49,14 @@ template void launch_grid_update<3>(const Params &, float, GridPtrs<3>, cudaStre
 // ------------------------------------------------------------------------------------------------
 // naive P2G: one thread per particle, 3^D vector REDs (RED.E.ADD.F32x4) into L2.
 // ------------------------------------------------------------------------------------------------
-template <int D>
+template <int D, bool MIG>
 __global__ void __launch_bounds__(128) k_p2g_naive(Params P, float dt, SoA<D> s, long long first, long long n,
                                                    float4 *__restrict__ grid, int *__restrict__ status) {
   long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   PState<D> p;
   load_full(s, i, p);
-  if (p.mat == DEAD) return;
+  if (MIG && p.mat == DEAD) return;  // x-slab runs only: slot of an emigrated particle
   Stencil<D> st = make_stencil<D>(p.x, P.inv_dx);
   int bad = clamp_base<D>(P, st.base);
   if (bad) atomicOr(status, bad);
@@ -84,7 +84,8 @@ void launch_p2g_naive(const Params &P, float dt, const SoA<D> &s, long long firs
                       int *status, cudaStream_t st) {
   if (n - first <= 0) return;
   unsigned blocks = (unsigned)((n - first + 127) / 128);
-  k_p2g_naive<D><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, status);
+  if (P.multi) k_p2g_naive<D, true><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, status);
+  else k_p2g_naive<D, false><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, status);
 }
 template void launch_p2g_naive<2>(const Params &, float, const SoA<2> &, long long, long long, GridPtrs<2>, int *,
                                   cudaStream_t);
@@ -156,7 +157,7 @@ __device__ __forceinline__ void red_node(const Params &P, float4 *grid, int i, i
 #ifndef MPM_P2G_MINB
 #define MPM_P2G_MINB 8
 #endif
-template <int D, int B, int NT, int CAP, int TPC, bool FAST>
+template <int D, int B, int NT, int CAP, int TPC, bool FAST, bool MIG>
 __global__ void __launch_bounds__(NT, MPM_P2G_MINB) k_p2g_cells(Params P, BinGeom G, float dt, SoA<D> s,
                                                   const int *__restrict__ bin_start, float4 *__restrict__ grid,
                                                   int *__restrict__ status, unsigned long long *__restrict__ stats) {
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(NT, MPM_P2G_MINB) k_p2g_cells(Params P, BinGeo
     for (int i = tid; i < m; i += NT) {
       PState<D> p;
       load_full(s, (long long)c0 + i, p);
-      if (p.mat == DEAD) {  // emigrated to a neighbouring slab since the last re-sort
+      if (MIG && p.mat == DEAD) {  // x-slab runs only: emigrated since the last re-sort
         cell_of[i] = 0xffffu;
         continue;
       }
@@ -390,7 +391,10 @@ __global__ void __launch_bounds__(NT, MPM_P2G_MINB) k_p2g_cells(Params P, BinGeo
     }
     __syncthreads();
   }
-  if (stats && n_fallback) atomicAdd(&stats[0], (unsigned long long)n_fallback);
+  if (stats && n_fallback) {
+    atomicAdd(&stats[0], (unsigned long long)n_fallback);
+    atomicAdd(&stats[1], (unsigned long long)n_fallback);
+  }
 }
 
 template <int D>
@@ -405,11 +409,23 @@ void launch_p2g_cells(const Params &P, const BinGeom &G, float dt, const SoA<D> 
                       GridPtrs<D> g, int *status, unsigned long long *stats, bool strict, cudaStream_t st) {
   if (n <= 0) return;
   if constexpr (D == 2) {
-    if (strict) k_p2g_cells<2, 8, 128, 768, 1, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
-    else k_p2g_cells<2, 8, 128, 768, 1, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+    if (strict) {
+      if (P.multi) k_p2g_cells<2, 8, 128, 768, 1, false, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+      else k_p2g_cells<2, 8, 128, 768, 1, false, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+    }
+    else {
+      if (P.multi) k_p2g_cells<2, 8, 128, 768, 1, true, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+      else k_p2g_cells<2, 8, 128, 768, 1, true, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+    }
   } else {
-    if (strict) k_p2g_cells<3, 4, 128, 512, 3, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
-    else k_p2g_cells<3, 4, 128, 512, 3, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+    if (strict) {
+      if (P.multi) k_p2g_cells<3, 4, 128, 512, 3, false, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+      else k_p2g_cells<3, 4, 128, 512, 3, false, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+    }
+    else {
+      if (P.multi) k_p2g_cells<3, 4, 128, 512, 3, true, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+      else k_p2g_cells<3, 4, 128, 512, 3, true, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
+    }
   }
 }
 template void launch_p2g_cells<2>(const Params &, const BinGeom &, float, const SoA<2> &, long long, const int *,
@@ -420,7 +436,9 @@ template void launch_p2g_cells<3>(const Params &, const BinGeom &, float, const 
 // ------------------------------------------------------------------------------------------------
 // naive G2P: one thread per particle, 3^D node reads through the read-only path, in-place update.
 // ------------------------------------------------------------------------------------------------
-template <int D>
+// NOTE: no min-blocks hint here on purpose: with one, ptxas front-loads all 3^D node loads (56 regs),
+// which measured 14% slower on B200 than the interleaved schedule it picks without (48 regs).
+template <int D, bool MIG>
 __global__ void __launch_bounds__(128) k_g2p_naive(Params P, float dt, SoA<D> s, long long n,
                                                    const float4 *__restrict__ grid, const void *__restrict__ vold_,
                                                    MigPtrs mig, int *__restrict__ status) {
@@ -429,7 +447,7 @@ __global__ void __launch_bounds__(128) k_g2p_naive(Params P, float dt, SoA<D> s,
   const bool flip = P.alpha != 0.0f;
   PState<D> p;
   load_g2p(s, i, p, flip);
-  if (p.mat == DEAD) return;
+  const bool dead = MIG && p.mat == DEAD;  // predicate, not an early exit: keeps every load in flight
   Stencil<D> st = make_stencil<D>(p.x, P.inv_dx);
   clamp_base<D>(P, st.base);
   const Material &mat = P.mat[material_index(P, p.mat)];
@@ -466,7 +484,8 @@ __global__ void __launch_bounds__(128) k_g2p_naive(Params P, float dt, SoA<D> s,
   for (int c = 0; c < D; c++) p.v[c] = v[c];
   p.C = C;
   g2p_finish<D>(P, mat, dt, p.x, p.v, p.C, p.F, p.Jp, v_in, dv);
-  if (mig.enabled) {
+  if (dead) return;
+  if (MIG) {
     // x-slab ownership follows the base cell of the NEW position (what the next P2G will use, :55)
     int bx = base_coord(p.x[0], P.inv_dx);
     bx = max(0, min(bx, P.n_grid - 2));
@@ -511,7 +530,8 @@ void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long n, G
                       cudaStream_t st) {
   if (n <= 0) return;
   unsigned blocks = (unsigned)((n + 127) / 128);
-  k_g2p_naive<D><<<blocks, 128, 0, st>>>(P, dt, s, n, g.g, g.vold, mig, status);
+  if (mig.enabled) k_g2p_naive<D, true><<<blocks, 128, 0, st>>>(P, dt, s, n, g.g, g.vold, mig, status);
+  else k_g2p_naive<D, false><<<blocks, 128, 0, st>>>(P, dt, s, n, g.g, g.vold, mig, status);
 }
 template void launch_g2p_naive<2>(const Params &, float, const SoA<2> &, long long, GridPtrs<2>, MigPtrs, int *,
                                   cudaStream_t);

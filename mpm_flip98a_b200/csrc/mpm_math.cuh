@@ -48,6 +48,7 @@ struct Params {
   Material mat[4];
   int slab_lo, slab_hi;  // owned base-cell columns [lo, hi)
   int ncol;              // local node columns = slab_hi - slab_lo + 2
+  int multi;             // 1 when the slab is a strict part of the grid (dead slots, migration)
 };
 
 template <int D>

@@ -32,11 +32,12 @@ __global__ void k_bin_keys(Params P, BinGeom G, SoA<D> s, long long n, int *__re
 #pragma unroll
   for (int k = 0; k < D; k++) base[k] = base_coord(x[k], P.inv_dx);
   int bad = clamp_base<D>(P, base);
-  if (bad && load_mat(s, i) != DEAD) atomicOr(status, bad);
+  const bool dead = P.multi && load_mat(s, i) == DEAD;
+  if (bad && !dead) atomicOr(status, bad);
   unsigned kk = (unsigned)((base[0] - P.slab_lo) / G.edge);
 #pragma unroll
   for (int k = 1; k < D; k++) kk = kk * (unsigned)G.nb[k] + (unsigned)(base[k] / G.edge);
-  if (load_mat(s, i) == DEAD) kk = (unsigned)G.n_bins;  // emigrated: sorts behind every live particle
+  if (dead) kk = (unsigned)G.n_bins;  // emigrated: sorts behind every live particle
   const long long o = by_id ? (long long)s.id[i] : i;  // by_id: outputs indexed by upload order
   key[o] = kk;
   if (cell) {

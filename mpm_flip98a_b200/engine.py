@@ -57,7 +57,7 @@ class MigrationDesc(ctypes.Structure):
 
 class Profile(ctypes.Structure):
     _fields_ = [("ms", ctypes.c_double * 8), ("launches", ctypes.c_longlong * 8), ("substeps", ctypes.c_longlong),
-                ("fallback_particles", ctypes.c_longlong)]
+                ("fallback_particles", ctypes.c_longlong), ("rebin_interval", ctypes.c_longlong)]
 
 
 PHASES = ("clear", "p2g", "grid", "g2p", "bin", "halo", "migrate")
@@ -105,7 +105,11 @@ def load_library(path=None):
                                 "or `make -C mpm_flip98a_b200/csrc`" % p)
     lib = ctypes.CDLL(p)
     for name, (res, args) in SYMBOLS.items():
-        f = getattr(lib, name)
+        f = getattr(lib, name, None)
+        if f is None:
+            if os.environ.get("MPM_LIBRARY"):  # A/B runs against an older build
+                continue
+            raise ImportError("%s does not export %s" % (p, name))
         f.restype = res
         f.argtypes = args
     if lib.mpm_config_bytes() != ctypes.sizeof(Config):
@@ -258,6 +262,7 @@ class Engine:
         out = {name: (pr.ms[i], pr.launches[i]) for i, name in enumerate(PHASES)}
         out["substeps"] = pr.substeps
         out["fallback_particles"] = pr.fallback_particles
+        out["rebin_interval"] = pr.rebin_interval
         return out
 
     def grid_shape(self):
