@@ -275,8 +275,15 @@ def make_line(args, world, n_total, n_local, words, dim, n_grid, alpha, dt, desc
     dom_ms = phases[dom][0] / max(1, prof["substeps"])
     achieved = algo[dom] * n_local / (dom_ms * 1e-3) / 1e9  # per launch == this rank's particles
     whole = (algo["p2g"] + algo["g2p"]) * value / world / 1e9  # per GPU
+    traffic = None
+    try:  # measured DRAM bytes per launch of that kernel (ncu --set full, see profiles/), same particle count
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {})
+        if abs(t.get("particles", -1) - n_local) <= 0.01 * n_local:
+            traffic = t.get(dom)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_kind,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_kind,
                 "algorithmic_bytes_per_particle": algo[dom], "kernel_ms": dom_ms,
                 "whole_substep": {"algorithmic_bytes_per_particle": algo["p2g"] + algo["g2p"],
                                   "achieved": whole, "frac": whole / peak, "frac_of_nominal_8TBs": whole / 8000.0},
