@@ -322,7 +322,7 @@ def run_slabs(args, rank, world, local):
     align = 8 * world
     n_grid = int(round(n0 * world ** 0.5 / align)) * align
     dt, vol = scenes.scaled_constants(n_grid, dim)
-    slabs = parallel.partition(n_grid, world, 8)
+    slabs = parallel.partition_filled(n_grid, world, 8, x_range=(0.05, 0.95))  # equal particle counts
     lo, hi = slabs[rank]
     dev = "cuda:%d" % local
     # this rank's particles: generate the cell columns that can hold owned base cells, keep the owned
@@ -351,7 +351,7 @@ def run_slabs(args, rank, world, local):
         up = lambda: eng._check(eng.lib.mpm_upload_particles_ids(eng.h, host.data_ptr(), ids.data_ptr(), n_local, 0))
         up()
         r = parallel.SlabRank(eng, rank, world, dev)
-        ex = parallel.DistExchange(r)
+        ex = parallel.DistExchange(r, shared_stream=True)  # engine and NCCL ops are ordered on `stream`
         parallel.step_dist(r, ex, args.warm_substeps)
         if eng.poll_status() != 0:
             raise SystemExit("rank %d: engine status after warm-up: %s" % (rank, eng.lib.mpm_last_error(eng.h)))
@@ -406,7 +406,8 @@ def run_slabs(args, rank, world, local):
     if rank == 0:
         line = make_line(args, world, n_total, n_local, 14, dim, n_grid, alpha, dt, descr, ms, value, e2e_value, prof,
                          clocks, scaling="weak",
-                         extra_config={"decomposition": "x-slabs, %d columns per GPU" % (hi - lo),
+                         extra_config={"decomposition": "x-slabs cut for equal particle counts, %d..%d columns per GPU"
+                                                        % (min(b - a for a, b in slabs), max(b - a for a, b in slabs)),
                                        "weak_scaling_rule": "n_grid = 8192*sqrt(N), same fill fractions: particles "
                                                             "and nodes per GPU as at N=1",
                                        "exchange": "NCCL P2P: 2 ghost node columns each way + emigrant records"})

@@ -26,6 +26,17 @@ def partition(n_grid, world, align=8):
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def partition_filled(n_grid, world, align=8, x_range=(0.05, 0.95)):
+    """Slabs that split the FILLED x-range evenly (equal particle counts for a uniform fill); the first
+    and last slab additionally own the empty margins.  Same conventions as partition()."""
+    if world == 1:
+        return [(0, n_grid)]
+    lo, hi = x_range[0] * n_grid, x_range[1] * n_grid
+    cuts = [0] + [int(round((lo + (hi - lo) * r / world) / align)) * align for r in range(1, world)] + [n_grid]
+    assert all(b - a >= align for a, b in zip(cuts[:-1], cuts[1:])), "grid too small for %d slabs" % world
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def base_column(x, n_grid):
     """Base cell x-index exactly as the engine computes it (fp32 multiply, subtract, truncate)."""
     inv_dx = np.float32(1.0) / (np.float32(1.0) / np.float32(n_grid))
@@ -137,9 +148,11 @@ class LocalExchange:
 class DistExchange:
     """One slab per process: torch.distributed point-to-point with the two x-neighbours."""
 
-    def __init__(self, rank_obj, group=None):
+    def __init__(self, rank_obj, group=None, shared_stream=False):
+        """shared_stream: the engine launches on torch's CURRENT stream (mpm_config.stream), so the
+        P2P ops are stream-ordered against its kernels and no host synchronisation is needed around them."""
         import torch.distributed as dist
-        self.r, self.dist, self.group = rank_obj, dist, group
+        self.r, self.dist, self.group, self.shared = rank_obj, dist, group, shared_stream
 
     def _run(self, ops):
         if ops:
@@ -148,7 +161,8 @@ class DistExchange:
 
     def halo(self):
         r, d = self.r, self.dist
-        r.e.synchronize()  # P2G wrote the send columns on the engine's stream
+        if not self.shared:
+            r.e.synchronize()  # P2G wrote the send columns on the engine's own stream
         ops = []
         if r.has_hi:
             ops += [d.P2POp(d.isend, r.halo_send_hi, r.rank + 1, self.group),
@@ -193,7 +207,7 @@ class DistExchange:
 
     def _sync(self):
         import torch
-        if self.r.device != "cpu" and torch.cuda.is_available():
+        if not self.shared and self.r.device != "cpu" and torch.cuda.is_available():
             torch.cuda.synchronize()
 
 

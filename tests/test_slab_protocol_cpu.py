@@ -20,6 +20,11 @@ def test_partition_and_ownership():
         assert slabs[0][0] == 0 and slabs[-1][1] == n and len(slabs) == w
         for (a, b), (c, d) in zip(slabs[:-1], slabs[1:]):
             assert b == c and a % align == 0 and b - a >= align
+    for n, w in ((8192, 8), (23168, 8), (512, 4)):
+        slabs = parallel.partition_filled(n, w)
+        assert slabs[0][0] == 0 and slabs[-1][1] == n and all(a % 8 == 0 for a, _ in slabs)
+        filled = [min(b, 0.95 * n) - max(a, 0.05 * n) for a, b in slabs]
+        assert max(filled) - min(filled) <= 16  # equal shares of the filled range, up to alignment
     p = scenes.commented_three_blocks()
     slabs = parallel.partition(80, 4)
     own = parallel.owner_of(p[:, 0], 80, slabs)
