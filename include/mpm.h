@@ -52,9 +52,15 @@ enum {
   MPM_FLAG_CAPTURE_POST_P2G = 1 << 0, /* keep a copy of the grid between P2G and the grid update */
   MPM_FLAG_NAIVE = 1 << 1,            /* one-thread-per-particle kernels with global atomics
                                          (no binning); the small-scene / debugging path */
-  MPM_FLAG_STRICT = 1 << 2            /* binned P2G forms every node contribution in the reference's
-                                         exact association order (:92-100) instead of the separable
-                                         FMA form (algebraically identical, ~1e-7 relative apart) */
+  MPM_FLAG_G2P_TILE = 1 << 3,         /* binned path: G2P stages each bin's node tile in shared memory
+                                         (measured no faster than the read-only-path gather: off by default) */
+  MPM_FLAG_NO_FUSE = 1 << 4,          /* keep P2G and G2P as separate kernels (default on one GPU: G2P of a
+                                         substep and P2G of the next run fused, one particle read + one
+                                         write per substep; x-slab handles always run unfused) */
+  MPM_FLAG_STRICT = 1 << 2            /* binned path: P2G node contributions (:92-100) and the G2P gather
+                                         (:153-154) keep the reference's exact association instead of the
+                                         separable / hoisted FMA forms (algebraically identical, ~1e-7
+                                         relative apart).  MPM_FLAG_NAIVE is always exact. */
 };
 
 /* Everything the reference fixes at compile time (:8-26, :113, :116, :169, :175) plus the
@@ -148,6 +154,8 @@ typedef struct mpm_profile {
   long long fallback_particles; /* binned P2G: particles that had drifted past the bin margin and
                                    took the per-particle scatter instead (correct, just slower) */
   long long rebin_interval;     /* substeps between storage re-sorts right now */
+  long long fused_substeps;     /* substeps whose G2P ran fused with the next P2G (its time is under
+                                   MPM_PHASE_G2P; MPM_PHASE_P2G then only holds stand-alone P2G launches) */
 } mpm_profile;
 int mpm_profile_enable(mpm_handle *h, int on); /* (re)starts accumulation from zero */
 int mpm_profile_read(mpm_handle *h, mpm_profile *out); /* synchronises */

@@ -43,6 +43,11 @@ struct mpm_handle {
 
   // grid
   float4 *grid = nullptr, *grid_tap = nullptr;
+  // fused G2P->P2G (single-GPU binned path): the P2G of the NEXT substep lands in grid_next while G2P reads
+  // `grid`; the two swap each substep.  grid_read = the buffer that holds the last UPDATED grid (mpm_read_grid).
+  float4 *grid_next = nullptr, *grid_read = nullptr;
+  bool fused = false, p2g_ready = false;
+  float p2g_dt = 0.0f;
   void *vold = nullptr;
   long long nodes = 0;
   bool tap_valid = false;
@@ -163,6 +168,7 @@ struct mpm_handle {
   int substep(float dt, int n_steps);
   int step_p2g(float dt);
   int step_grid_g2p(float dt);
+  int step_fused(float dt);
   int read_grid(int stage, float *out);
   int bin_particles(int *cell, int *key, int *order, int *bin_start_out);
   int poll_status();
@@ -258,6 +264,7 @@ int mpm_handle::init() {
   nodes = (long long)P.ncol * P.n1 * (D == 3 ? P.n1 : 1);
   int rc;
   if ((rc = dalloc(&grid, (size_t)nodes))) return rc;
+  grid_read = grid;
   if (cfg.alpha != 0.0f) {
     char *v;
     if ((rc = dalloc(&v, (size_t)nodes * (D == 2 ? 8 : 16)))) return rc;
@@ -309,6 +316,10 @@ int mpm_handle::init() {
     mig_count_host[0] = mig_count_host[1] = 0;
   }
   binned = !(cfg.flags & MPM_FLAG_NAIVE) && (D == 2 ? p2g_cells_supported<2>(G) : p2g_cells_supported<3>(G));
+  // 2D only: in 3D the Jacobi-SVD-heavy kernels are compute-bound and fusing them costs occupancy (measured slower)
+  fused = binned && !multi && D == 2 && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE));
+  if (fused)
+    if ((rc = dalloc(&grid_next, (size_t)nodes))) return rc;
 
   stage_records = cap < (1LL << 22) ? cap : (1LL << 22);  // <= 4M records (224 / 416 MB) per chunk
   if ((rc = dalloc(&stage, (size_t)stage_records * record_words()))) return rc;
@@ -351,6 +362,7 @@ int mpm_handle::upload(const void *aos, const int *ids, long long count, int on_
   MPM_CUDA(cudaGetLastError());
   n = count;
   live = count;
+  p2g_ready = false;
   tap_valid = false;
   mig_counts_valid = false;
   int rc = rebin_storage();
@@ -420,6 +432,8 @@ int mpm_handle::read(void *aos_out, long long count, int to_device) {
 }
 
 int mpm_handle::step_p2g(float dt) {
+  p2g_ready = false;
+  grid_read = grid;
   {
     Phase ph(this, MPM_PHASE_CLEAR, 0);
     MPM_CUDA(cudaMemsetAsync(grid, 0, (size_t)nodes * sizeof(float4), stream));  // :50
@@ -452,14 +466,63 @@ int mpm_handle::step_grid_g2p(float dt) {
   {
     Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
     if (multi) MPM_CUDA(cudaMemsetAsync(mig.count, 0, 8, stream));
-    if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], n, gp<2>(), mig, status_dev, stream);
-    else launch_g2p_naive<3>(P, dt, s3[cur], n, gp<3>(), mig, status_dev, stream);
+    // exact association everywhere under MPM_FLAG_STRICT and on the naive path (the bit-faithful modes)
+    const bool strict = (cfg.flags & (MPM_FLAG_STRICT | MPM_FLAG_NAIVE)) != 0;
+    if (binned && (cfg.flags & MPM_FLAG_G2P_TILE)) {
+      if (D == 2) launch_g2p_bins<2>(P, G, dt, s2[cur], n_binned, bin_start, gp<2>(), mig, status_dev, strict, stream);
+      else launch_g2p_bins<3>(P, G, dt, s3[cur], n_binned, bin_start, gp<3>(), mig, status_dev, strict, stream);
+      // immigrants since the last re-sort sit behind the binned range
+      if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
+      else launch_g2p_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), mig, status_dev, strict, stream);
+    } else {
+      if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), mig, status_dev, strict, stream);
+      else launch_g2p_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), mig, status_dev, strict, stream);
+    }
     if (multi) {
       MPM_CUDA(cudaMemcpyAsync(mig_count_host, mig.count, 8, cudaMemcpyDeviceToHost, stream));
       mig_counts_valid = true;
     }
   }
   if (prof_on) prof.substeps++;
+  return MPM_OK;
+}
+
+// One substep on the fused schedule: [P2G only if the grid does not already hold it] -> grid update ->
+// fused kernel: G2P of this substep + P2G of the next one into the other grid buffer.
+int mpm_handle::step_fused(float dt) {
+  if (!p2g_ready || p2g_dt != dt) {
+    int rc = step_p2g(dt);  // clear + standalone binned P2G into `grid`
+    if (rc) return rc;
+  }
+  if (grid_tap) {
+    MPM_CUDA(cudaMemcpyAsync(grid_tap, grid, (size_t)nodes * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
+    tap_valid = true;
+  }
+  {
+    Phase ph(this, MPM_PHASE_GRID, 1);
+    if (D == 2) launch_grid_update<2>(P, dt, gp<2>(), stream);
+    else launch_grid_update<3>(P, dt, gp<3>(), stream);
+  }
+  {
+    Phase ph(this, MPM_PHASE_CLEAR, 0);
+    MPM_CUDA(cudaMemsetAsync(grid_next, 0, (size_t)nodes * sizeof(float4), stream));  // :50 of the next substep
+  }
+  {
+    Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
+    const bool strict = (cfg.flags & MPM_FLAG_STRICT) != 0;
+    if (D == 2) launch_g2p2g<2>(P, G, dt, dt, s2[cur], n, bin_start, gp<2>(), grid_next, status_dev, stats_dev, strict, stream);
+    else launch_g2p2g<3>(P, G, dt, dt, s3[cur], n, bin_start, gp<3>(), grid_next, status_dev, stats_dev, strict, stream);
+  }
+  grid_read = grid;  // the updated grid of this substep
+  float4 *t = grid;
+  grid = grid_next;
+  grid_next = t;
+  p2g_ready = true;
+  p2g_dt = dt;
+  if (prof_on) {
+    prof.substeps++;
+    prof.fused_substeps++;
+  }
   return MPM_OK;
 }
 
@@ -479,8 +542,12 @@ int mpm_handle::substep(float dt, int n_steps) {
     const int every = current_interval();
     if (every > 0 && steps_since_sort >= every)
       if ((rc = rebin_storage())) return rc;
-    if ((rc = step_p2g(dt))) return rc;
-    if ((rc = step_grid_g2p(dt))) return rc;
+    if (fused) {
+      if ((rc = step_fused(dt))) return rc;
+    } else {
+      if ((rc = step_p2g(dt))) return rc;
+      if ((rc = step_grid_g2p(dt))) return rc;
+    }
     steps_since_sort++;
   }
   MPM_CUDA(cudaGetLastError());
@@ -498,7 +565,7 @@ int mpm_handle::read_grid(int stage_id, float *out) {
   }
   MPM_CUDA(cudaSetDevice(cfg.device));
   std::vector<float4> host((size_t)nodes);
-  MPM_CUDA(cudaMemcpyAsync(host.data(), stage_id == 1 ? grid_tap : grid, (size_t)nodes * sizeof(float4),
+  MPM_CUDA(cudaMemcpyAsync(host.data(), stage_id == 1 ? grid_tap : grid_read, (size_t)nodes * sizeof(float4),
                            cudaMemcpyDeviceToHost, stream));
   MPM_CUDA(cudaStreamSynchronize(stream));
   for (long long i = 0; i < nodes; i++) {

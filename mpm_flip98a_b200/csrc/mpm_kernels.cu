@@ -93,6 +93,124 @@ template void launch_p2g_naive<3>(const Params &, float, const SoA<3> &, long lo
                                   cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
+// G2P building blocks (used by the G2P kernels below and by the fused G2P->P2G kernel)
+// ------------------------------------------------------------------------------------------------
+// One particle of G2P (:134-179).  `fetch(a, b, c, base, gv, vo)` delivers node velocity (and, for FLIP,
+// its pre-gravity value) of stencil offset (a,b,c): straight from L2/L1 (naive kernel) or from the
+// shared-memory tile of the particle's bin (binned kernel).
+// loads particle i, gathers from the grid and returns the NEW state in p (nothing stored yet)
+template <int D, bool FAST, typename Fetch>
+__device__ __forceinline__ void g2p_update(const Params &P, float dt, const SoA<D> &s, long long i, const Fetch &fetch,
+                                           PState<D> &p) {
+  const bool flip = P.alpha != 0.0f;
+  load_g2p(s, i, p, flip);
+  Stencil<D> st = make_stencil<D>(p.x, P.inv_dx);
+  clamp_base<D>(P, st.base);
+  const Material &mat = P.mat[material_index(P, p.mat)];
+  float v_in[D], dv[D], v[D];
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    v_in[c] = flip ? p.v[c] : 0.0f;
+    dv[c] = 0.0f;
+    v[c] = 0.0f;  // :145
+  }
+  Mat<D> C = mat_zero<D>();  // :144
+  constexpr bool FG = FAST && D == 2;  // 3D: the hoisted form measured slower (register pressure), keep :153-154 as is
+  fetch.template gather<FG>(P, st, flip, v, C, dv);
+  if (FG) {  // the 4*inv_dx of :154, applied once
+    const float s4 = 4 * P.inv_dx;
+#pragma unroll
+    for (int cc = 0; cc < D; cc++)
+#pragma unroll
+      for (int r = 0; r < D; r++) C.d[cc][r] = s4 * C.d[cc][r];
+  }
+#pragma unroll
+  for (int c = 0; c < D; c++) p.v[c] = v[c];
+  p.C = C;
+  g2p_finish<D>(P, mat, dt, p.x, p.v, p.C, p.F, p.Jp, v_in, dv);
+}
+
+template <int D, bool MIG, bool FAST, typename Fetch>
+__device__ __forceinline__ void g2p_one(const Params &P, float dt, const SoA<D> &s, long long i, const Fetch &fetch,
+                                        const MigPtrs &mig, int *__restrict__ status) {
+  PState<D> p;
+  g2p_update<D, FAST>(P, dt, s, i, fetch, p);
+  const bool dead = MIG && p.mat == DEAD;  // predicate after the loads were issued, not an early exit
+  if (dead) return;
+  if (MIG) {
+    // x-slab ownership follows the base cell of the NEW position (what the next P2G will use, :55)
+    int bx = base_coord(p.x[0], P.inv_dx);
+    bx = max(0, min(bx, P.n_grid - 2));
+    const int side = bx < P.slab_lo ? 0 : (bx >= P.slab_hi ? 1 : -1);
+    if (side >= 0) {
+      int slot = atomicAdd(&mig.count[side], 1);
+      if (slot < mig.cap) {
+        constexpr int W = MigRec<D>::WORDS;
+        float *r = (side == 0 ? mig.send_lo : mig.send_hi) + (size_t)slot * W;
+        float rec[W];
+#pragma unroll
+        for (int c = 0; c < D; c++) {
+          rec[c] = p.x[c];
+          rec[D + c] = p.v[c];
+        }
+#pragma unroll
+        for (int c = 0; c < D; c++)
+#pragma unroll
+          for (int k = 0; k < D; k++) {
+            rec[2 * D + c * D + k] = p.F.d[c][k];
+            rec[2 * D + D * D + c * D + k] = p.C.d[c][k];
+          }
+        rec[2 * D + 2 * D * D] = p.Jp;
+        rec[2 * D + 2 * D * D + 1] = __int_as_float(p.mat);
+        rec[W - 2] = __int_as_float(s.id[i]);
+        rec[W - 1] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < W / 4; k++)
+          reinterpret_cast<float4 *>(r)[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+        p.mat = DEAD;
+        mark_dead(s, i);
+      } else {
+        atomicOr(status, STATUS_MIGRATION_OVERFLOW);  // stays here (and will be flagged out of slab)
+      }
+    }
+  }
+  store_state(s, i, p);
+}
+
+// nodes straight from global memory through the read-only path
+template <int D>
+struct GlobalFetch {
+  const float4 *__restrict__ grid;
+  const void *__restrict__ vold_;
+  template <bool FAST>
+  __device__ __forceinline__ void gather(const Params &P, const Stencil<D> &st, bool flip, float *v, Mat<D> &C,
+                                         float *dv) const {
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++)
+#pragma unroll
+        for (int c = 0; c < (D == 3 ? 3 : 1); c++) {
+          long long node = node_index<D>(P, st.base[0] + a, st.base[1] + b, D == 3 ? st.base[D - 1] + c : 0);
+          float4 g4 = __ldg(&grid[node]);
+          float gv[3] = {g4.x, g4.y, g4.z};
+          float vo[3] = {0.0f, 0.0f, 0.0f};
+          if (flip) {
+            if (D == 2) {
+              float2 o = __ldg(&((const float2 *)vold_)[node]);
+              vo[0] = o.x; vo[1] = o.y;
+            } else {
+              float4 o = __ldg(&((const float4 *)vold_)[node]);
+              vo[0] = o.x; vo[1] = o.y; vo[2] = o.z;
+            }
+          }
+          if (FAST) g2p_accumulate_fast<D>(st, a, b, c, gv, vo, flip, v, C, dv);
+          else g2p_accumulate<D>(P, st, a, b, c, gv, vo, flip, v, C, dv);
+        }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
 // binned P2G ("cell gather"): one CTA per bin of B^D cells.  No floating-point atomics in shared
 // memory (on sm_100a atomicAdd(float) on shared is a CAS loop, ATOMS.CAST.SPIN) and no shuffles:
 //   phase 1  thread per particle (coalesced SoA loads): stencil, stress, affine (:55-89) -> a compact
@@ -157,10 +275,18 @@ __device__ __forceinline__ void red_node(const Params &P, float4 *grid, int i, i
 #ifndef MPM_P2G_MINB
 #define MPM_P2G_MINB 8
 #endif
-template <int D, int B, int NT, int CAP, int TPC, bool FAST, bool MIG>
-__global__ void __launch_bounds__(NT, MPM_P2G_MINB) k_p2g_cells(Params P, BinGeom G, float dt, SoA<D> s,
-                                                  const int *__restrict__ bin_start, float4 *__restrict__ grid,
-                                                  int *__restrict__ status, unsigned long long *__restrict__ stats) {
+#ifndef MPM_FUSED_MINB
+#define MPM_FUSED_MINB 6
+#endif
+// FUSED: phase 1 first runs G2P of the CURRENT substep on the particle (gather from `grid_in`, the
+// updated grid; new state stored in place) and then forms the P2G record of the NEXT substep from the
+// state it still holds in registers: each particle is read once and written once per substep
+// (84 B instead of 140 B of HBM traffic) and P2G never waits on particle loads.
+template <int D, int B, int NT, int CAP, int TPC, bool FAST, bool MIG, bool FUSED>
+__global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : MPM_P2G_MINB)
+    k_p2g_cells(Params P, BinGeom G, float dt, SoA<D> s, const int *__restrict__ bin_start, float4 *__restrict__ grid,
+                int *__restrict__ status, unsigned long long *__restrict__ stats, const float4 *__restrict__ grid_in,
+                const void *__restrict__ vold_in, float dt_g2p) {
   constexpr int M = 1, L = B + 2 * M;
   constexpr int NC = D == 2 ? L * L : L * L * L;
   __shared__ CellRec<D> rec[CAP];
@@ -191,7 +317,13 @@ __global__ void __launch_bounds__(NT, MPM_P2G_MINB) k_p2g_cells(Params P, BinGeo
     // ---- phase 1: thread per particle ----
     for (int i = tid; i < m; i += NT) {
       PState<D> p;
-      load_full(s, (long long)c0 + i, p);
+      if (FUSED) {
+        GlobalFetch<D> fetch{grid_in, vold_in};
+        g2p_update<D, FAST>(P, dt_g2p, s, (long long)c0 + i, fetch, p);  // :134-179 of this substep
+        store_state(s, (long long)c0 + i, p);
+      } else {
+        load_full(s, (long long)c0 + i, p);
+      }
       if (MIG && p.mat == DEAD) {  // x-slab runs only: emigrated since the last re-sort
         cell_of[i] = 0xffffu;
         continue;
@@ -404,28 +536,28 @@ bool p2g_cells_supported(const BinGeom &G) {
 template bool p2g_cells_supported<2>(const BinGeom &);
 template bool p2g_cells_supported<3>(const BinGeom &);
 
+template <int D, bool FAST, bool MIG, bool FUSED>
+static void launch_cells_variant(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, const int *bin_start,
+                                 float4 *grid, int *status, unsigned long long *stats, const float4 *grid_in,
+                                 const void *vold_in, float dt_g2p, cudaStream_t st) {
+  if constexpr (D == 2)
+    k_p2g_cells<2, 8, 128, 768, 1, FAST, MIG, FUSED><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, grid, status, stats,
+                                                                            grid_in, vold_in, dt_g2p);
+  else
+    k_p2g_cells<3, 4, 128, 512, 3, FAST, MIG, FUSED><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, grid, status, stats,
+                                                                            grid_in, vold_in, dt_g2p);
+}
+
 template <int D>
 void launch_p2g_cells(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, long long n, const int *bin_start,
                       GridPtrs<D> g, int *status, unsigned long long *stats, bool strict, cudaStream_t st) {
   if (n <= 0) return;
-  if constexpr (D == 2) {
-    if (strict) {
-      if (P.multi) k_p2g_cells<2, 8, 128, 768, 1, false, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
-      else k_p2g_cells<2, 8, 128, 768, 1, false, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
-    }
-    else {
-      if (P.multi) k_p2g_cells<2, 8, 128, 768, 1, true, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
-      else k_p2g_cells<2, 8, 128, 768, 1, true, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
-    }
+  if (strict) {
+    if (P.multi) launch_cells_variant<D, false, true, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, st);
+    else launch_cells_variant<D, false, false, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, st);
   } else {
-    if (strict) {
-      if (P.multi) k_p2g_cells<3, 4, 128, 512, 3, false, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
-      else k_p2g_cells<3, 4, 128, 512, 3, false, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
-    }
-    else {
-      if (P.multi) k_p2g_cells<3, 4, 128, 512, 3, true, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
-      else k_p2g_cells<3, 4, 128, 512, 3, true, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, status, stats);
-    }
+    if (P.multi) launch_cells_variant<D, true, true, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, st);
+    else launch_cells_variant<D, true, false, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, st);
   }
 }
 template void launch_p2g_cells<2>(const Params &, const BinGeom &, float, const SoA<2> &, long long, const int *,
@@ -433,110 +565,175 @@ template void launch_p2g_cells<2>(const Params &, const BinGeom &, float, const 
 template void launch_p2g_cells<3>(const Params &, const BinGeom &, float, const SoA<3> &, long long, const int *,
                                   GridPtrs<3>, int *, unsigned long long *, bool, cudaStream_t);
 
+// fused G2P(dt_g2p, reading g_in) + P2G(dt_p2g, scattering into grid_out); single-GPU handles only
+template <int D>
+void launch_g2p2g(const Params &P, const BinGeom &G, float dt_g2p, float dt_p2g, const SoA<D> &s, long long n,
+                  const int *bin_start, GridPtrs<D> g_in, float4 *grid_out, int *status, unsigned long long *stats,
+                  bool strict, cudaStream_t st) {
+  if (n <= 0) return;
+  if (strict) launch_cells_variant<D, false, false, true>(P, G, dt_p2g, s, bin_start, grid_out, status, stats, g_in.g, g_in.vold, dt_g2p, st);
+  else launch_cells_variant<D, true, false, true>(P, G, dt_p2g, s, bin_start, grid_out, status, stats, g_in.g, g_in.vold, dt_g2p, st);
+}
+template void launch_g2p2g<2>(const Params &, const BinGeom &, float, float, const SoA<2> &, long long, const int *,
+                              GridPtrs<2>, float4 *, int *, unsigned long long *, bool, cudaStream_t);
+template void launch_g2p2g<3>(const Params &, const BinGeom &, float, float, const SoA<3> &, long long, const int *,
+                              GridPtrs<3>, float4 *, int *, unsigned long long *, bool, cudaStream_t);
+
 // ------------------------------------------------------------------------------------------------
 // naive G2P: one thread per particle, 3^D node reads through the read-only path, in-place update.
 // ------------------------------------------------------------------------------------------------
 // NOTE: no min-blocks hint here on purpose: with one, ptxas front-loads all 3^D node loads (56 regs),
 // which measured 14% slower on B200 than the interleaved schedule it picks without (48 regs).
-template <int D, bool MIG>
-__global__ void __launch_bounds__(128) k_g2p_naive(Params P, float dt, SoA<D> s, long long n,
+template <int D, bool MIG, bool FAST>
+__global__ void __launch_bounds__(128) k_g2p_naive(Params P, float dt, SoA<D> s, long long first, long long n,
                                                    const float4 *__restrict__ grid, const void *__restrict__ vold_,
                                                    MigPtrs mig, int *__restrict__ status) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const bool flip = P.alpha != 0.0f;
-  PState<D> p;
-  load_g2p(s, i, p, flip);
-  const bool dead = MIG && p.mat == DEAD;  // predicate, not an early exit: keeps every load in flight
-  Stencil<D> st = make_stencil<D>(p.x, P.inv_dx);
-  clamp_base<D>(P, st.base);
-  const Material &mat = P.mat[material_index(P, p.mat)];
-  float v_in[D], dv[D], v[D];
+  GlobalFetch<D> fetch{grid, vold_};
+  g2p_one<D, MIG, FAST>(P, dt, s, i, fetch, mig, status);
+}
+
+// ------------------------------------------------------------------------------------------------
+// binned G2P: one CTA per bin stages the (B+4)^D node velocities its particles can touch (bin + 1-cell
+// drift margin + stencil reach) in shared memory once, instead of 3^D global loads per particle.
+// A particle that drifted past the margin since the last re-sort gathers from global memory.
+// ------------------------------------------------------------------------------------------------
+template <int D, int B, bool FLIP>
+struct TileFetch {
+  static constexpr int T = B + 4;
+  const float4 *tile;   // (vx, vy, vold_x, vold_y) in 2D; (vx, vy, vz, -) in 3D
+  const float4 *tile_o; // 3D FLIP only: (vold_x, vold_y, vold_z, -)
+  int o[3];             // global coordinate of tile node (0,0,0)
+  GlobalFetch<D> global;
+  template <bool FAST>
+  __device__ __forceinline__ void gather(const Params &P, const Stencil<D> &st, bool flip, float *v, Mat<D> &C,
+                                         float *dv) const {
+    const int l0 = st.base[0] - o[0], l1 = st.base[1] - o[1], l2 = D == 3 ? st.base[D - 1] - o[2] : 0;
+    const bool inside = (unsigned)l0 <= (unsigned)(T - 3) && (unsigned)l1 <= (unsigned)(T - 3) &&
+                        (D == 2 || (unsigned)l2 <= (unsigned)(T - 3));
+    if (!inside) {
+      global.template gather<FAST>(P, st, flip, v, C, dv);
+      return;
+    }
+    const int at = D == 2 ? l0 * T + l1 : (l0 * T + l1) * T + l2;
 #pragma unroll
-  for (int c = 0; c < D; c++) {
-    v_in[c] = flip ? p.v[c] : 0.0f;
-    dv[c] = 0.0f;
-    v[c] = 0.0f;  // :145
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+      for (int b = 0; b < 3; b++)
+#pragma unroll
+        for (int c = 0; c < (D == 3 ? 3 : 1); c++) {
+          const int k = D == 2 ? at + a * T + b : at + (a * T + b) * T + c;
+          float4 g4 = tile[k];
+          float gv[3] = {g4.x, g4.y, g4.z};
+          float vo[3] = {0.0f, 0.0f, 0.0f};
+          if (FLIP) {
+            if (D == 2) {
+              vo[0] = g4.z; vo[1] = g4.w;
+            } else {
+              float4 o4 = tile_o[k];
+              vo[0] = o4.x; vo[1] = o4.y; vo[2] = o4.z;
+            }
+          }
+          if (FAST) g2p_accumulate_fast<D>(st, a, b, c, gv, vo, FLIP, v, C, dv);
+          else g2p_accumulate<D>(P, st, a, b, c, gv, vo, FLIP, v, C, dv);
+        }
   }
-  Mat<D> C = mat_zero<D>();  // :144
-#pragma unroll
-  for (int a = 0; a < 3; a++)
-#pragma unroll
-    for (int b = 0; b < 3; b++)
-#pragma unroll
-      for (int c = 0; c < (D == 3 ? 3 : 1); c++) {
-        long long node = node_index<D>(P, st.base[0] + a, st.base[1] + b, D == 3 ? st.base[D - 1] + c : 0);
-        float4 g4 = __ldg(&grid[node]);
-        float gv[3] = {g4.x, g4.y, g4.z};
-        float vo[3] = {0.0f, 0.0f, 0.0f};
-        if (flip) {
-          if (D == 2) {
-            float2 o = __ldg(&((const float2 *)vold_)[node]);
-            vo[0] = o.x; vo[1] = o.y;
-          } else {
-            float4 o = __ldg(&((const float4 *)vold_)[node]);
-            vo[0] = o.x; vo[1] = o.y; vo[2] = o.z;
-          }
+};
+
+template <int D, int B, int NT, bool FLIP, bool MIG, bool FAST>
+__global__ void __launch_bounds__(NT) k_g2p_bins(Params P, BinGeom G, float dt, SoA<D> s, const int *__restrict__ bin_start,
+                                                 const float4 *__restrict__ grid, const void *__restrict__ vold_,
+                                                 MigPtrs mig, int *__restrict__ status) {
+  constexpr int T = B + 4, NN = D == 2 ? T * T : T * T * T;
+  __shared__ float4 tile[NN];
+  __shared__ float4 tile_o[(D == 3 && FLIP) ? NN : 1];
+  const int bin = blockIdx.x;
+  const int s0 = bin_start[bin], s1 = bin_start[bin + 1];
+  if (s0 >= s1) return;
+  TileFetch<D, B, FLIP> fetch;
+  {
+    int r = bin;
+    fetch.o[2] = 0;
+    if (D == 3) { fetch.o[2] = (r % G.nb[2]) * B - 1; r /= G.nb[2]; }
+    fetch.o[1] = (r % G.nb[1]) * B - 1;
+    fetch.o[0] = (r / G.nb[1]) * B + P.slab_lo - 1;
+  }
+  fetch.tile = tile;
+  fetch.tile_o = tile_o;
+  fetch.global = GlobalFetch<D>{grid, vold_};
+  for (int k = threadIdx.x; k < NN; k += NT) {
+    int l[3];
+    {
+      int r = k;
+      if (D == 3) { l[2] = r % T; r /= T; } else l[2] = 0;
+      l[1] = r % T;
+      l[0] = r / T;
+    }
+    const int gi = fetch.o[0] + l[0], gj = fetch.o[1] + l[1], gk = D == 3 ? fetch.o[2] + l[2] : 0;
+    float4 g4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), o4 = g4;
+    const bool ok = gi >= P.slab_lo && gi < P.slab_lo + P.ncol && gj >= 0 && gj < P.n1 && gk >= 0 && gk < P.n1;
+    if (ok) {
+      const long long node = node_index<D>(P, gi, gj, gk);
+      g4 = __ldg(&grid[node]);
+      if (FLIP) {
+        if (D == 2) {
+          float2 vo = __ldg(&((const float2 *)vold_)[node]);
+          g4.z = vo.x; g4.w = vo.y;
+        } else {
+          o4 = __ldg(&((const float4 *)vold_)[node]);
         }
-        g2p_accumulate<D>(P, st, a, b, c, gv, vo, flip, v, C, dv);
-      }
-#pragma unroll
-  for (int c = 0; c < D; c++) p.v[c] = v[c];
-  p.C = C;
-  g2p_finish<D>(P, mat, dt, p.x, p.v, p.C, p.F, p.Jp, v_in, dv);
-  if (dead) return;
-  if (MIG) {
-    // x-slab ownership follows the base cell of the NEW position (what the next P2G will use, :55)
-    int bx = base_coord(p.x[0], P.inv_dx);
-    bx = max(0, min(bx, P.n_grid - 2));
-    const int side = bx < P.slab_lo ? 0 : (bx >= P.slab_hi ? 1 : -1);
-    if (side >= 0) {
-      int slot = atomicAdd(&mig.count[side], 1);
-      if (slot < mig.cap) {
-        constexpr int W = MigRec<D>::WORDS;
-        float *r = (side == 0 ? mig.send_lo : mig.send_hi) + (size_t)slot * W;
-        float rec[W];
-#pragma unroll
-        for (int c = 0; c < D; c++) {
-          rec[c] = p.x[c];
-          rec[D + c] = p.v[c];
-        }
-#pragma unroll
-        for (int c = 0; c < D; c++)
-#pragma unroll
-          for (int k = 0; k < D; k++) {
-            rec[2 * D + c * D + k] = p.F.d[c][k];
-            rec[2 * D + D * D + c * D + k] = p.C.d[c][k];
-          }
-        rec[2 * D + 2 * D * D] = p.Jp;
-        rec[2 * D + 2 * D * D + 1] = __int_as_float(p.mat);
-        rec[W - 2] = __int_as_float(s.id[i]);
-        rec[W - 1] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < W / 4; k++)
-          reinterpret_cast<float4 *>(r)[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
-        p.mat = DEAD;
-        mark_dead(s, i);
-      } else {
-        atomicOr(status, STATUS_MIGRATION_OVERFLOW);  // stays here (and will be flagged out of slab)
       }
     }
+    tile[k] = g4;
+    if (D == 3 && FLIP) tile_o[k] = o4;
   }
-  store_state(s, i, p);
+  __syncthreads();
+  for (long long i = (long long)s0 + threadIdx.x; i < s1; i += NT) g2p_one<D, MIG, FAST>(P, dt, s, i, fetch, mig, status);
 }
 
 template <int D>
-void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long n, GridPtrs<D> g, MigPtrs mig, int *status,
-                      cudaStream_t st) {
+void launch_g2p_bins(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, long long n, const int *bin_start,
+                     GridPtrs<D> g, MigPtrs mig, int *status, bool strict, cudaStream_t st) {
   if (n <= 0) return;
-  unsigned blocks = (unsigned)((n + 127) / 128);
-  if (mig.enabled) k_g2p_naive<D, true><<<blocks, 128, 0, st>>>(P, dt, s, n, g.g, g.vold, mig, status);
-  else k_g2p_naive<D, false><<<blocks, 128, 0, st>>>(P, dt, s, n, g.g, g.vold, mig, status);
+  const bool flip = P.alpha != 0.0f;
+  constexpr int B = D == 2 ? 8 : 4;
+#define MPM_G2P_BINS(FLIP_, MIG_)                                                                                      \
+  {                                                                                                                    \
+    if (strict) k_g2p_bins<D, B, 128, FLIP_, MIG_, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, g.vold, mig, status); \
+    else k_g2p_bins<D, B, 128, FLIP_, MIG_, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, g.vold, mig, status);         \
+  }
+  if (flip) {
+    if (mig.enabled) MPM_G2P_BINS(true, true)
+    else MPM_G2P_BINS(true, false)
+  } else {
+    if (mig.enabled) MPM_G2P_BINS(false, true)
+    else MPM_G2P_BINS(false, false)
+  }
+#undef MPM_G2P_BINS
 }
-template void launch_g2p_naive<2>(const Params &, float, const SoA<2> &, long long, GridPtrs<2>, MigPtrs, int *,
-                                  cudaStream_t);
-template void launch_g2p_naive<3>(const Params &, float, const SoA<3> &, long long, GridPtrs<3>, MigPtrs, int *,
-                                  cudaStream_t);
+template void launch_g2p_bins<2>(const Params &, const BinGeom &, float, const SoA<2> &, long long, const int *,
+                                 GridPtrs<2>, MigPtrs, int *, bool, cudaStream_t);
+template void launch_g2p_bins<3>(const Params &, const BinGeom &, float, const SoA<3> &, long long, const int *,
+                                 GridPtrs<3>, MigPtrs, int *, bool, cudaStream_t);
+
+template <int D>
+void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long first, long long n, GridPtrs<D> g,
+                      MigPtrs mig, int *status, bool strict, cudaStream_t st) {
+  if (n - first <= 0) return;
+  unsigned blocks = (unsigned)((n - first + 127) / 128);
+  if (mig.enabled) {
+    if (strict) k_g2p_naive<D, true, false><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status);
+    else k_g2p_naive<D, true, true><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status);
+  } else {
+    if (strict) k_g2p_naive<D, false, false><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status);
+    else k_g2p_naive<D, false, true><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status);
+  }
+}
+template void launch_g2p_naive<2>(const Params &, float, const SoA<2> &, long long, long long, GridPtrs<2>, MigPtrs,
+                                  int *, bool, cudaStream_t);
+template void launch_g2p_naive<3>(const Params &, float, const SoA<3> &, long long, long long, GridPtrs<3>, MigPtrs,
+                                  int *, bool, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
 // x-slab exchange helpers: ghost-column sum, immigrant unpack

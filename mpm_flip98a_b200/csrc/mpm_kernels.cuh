@@ -22,8 +22,8 @@ template <int D>
 void launch_p2g_naive(const Params &P, float dt, const SoA<D> &s, long long first, long long n, GridPtrs<D> g,
                       int *status, cudaStream_t st);
 template <int D>
-void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long n, GridPtrs<D> g, MigPtrs mig, int *status,
-                      cudaStream_t st);
+void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long first, long long n, GridPtrs<D> g,
+                      MigPtrs mig, int *status, bool strict, cudaStream_t st);
 // x-slab exchange helpers
 void launch_halo_add(float4 *dst, const float4 *src, long long count, cudaStream_t st);
 template <int D>
@@ -37,6 +37,14 @@ bool p2g_cells_supported(const BinGeom &G);
 template <int D>
 void launch_p2g_cells(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, long long n, const int *bin_start,
                       GridPtrs<D> g, int *status, unsigned long long *stats, bool strict, cudaStream_t st);
+
+template <int D>
+void launch_g2p2g(const Params &P, const BinGeom &G, float dt_g2p, float dt_p2g, const SoA<D> &s, long long n,
+                  const int *bin_start, GridPtrs<D> g_in, float4 *grid_out, int *status, unsigned long long *stats,
+                  bool strict, cudaStream_t st);
+template <int D>
+void launch_g2p_bins(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, long long n, const int *bin_start,
+                     GridPtrs<D> g, MigPtrs mig, int *status, bool strict, cudaStream_t st);
 
 // ---- AoS <-> SoA at the C-ABI ------------------------------------------------------------------
 // records [first, first+count) of the caller's AoS -> SoA slots [first, first+count), id = index

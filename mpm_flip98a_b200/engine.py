@@ -17,6 +17,8 @@ KIND_FLUID, KIND_JELLY, KIND_SNOW = 0, 1, 2
 FLAG_CAPTURE_POST_P2G = 1
 FLAG_NAIVE = 2
 FLAG_STRICT = 4
+FLAG_G2P_TILE = 8
+FLAG_NO_FUSE = 16
 
 _ERRORS = {-1: "MPM_E_INVALID", -2: "MPM_E_CUDA", -3: "MPM_E_CAPACITY", -4: "MPM_E_DOMAIN", -5: "MPM_E_CFL",
            -6: "MPM_E_STATE"}
@@ -57,7 +59,8 @@ class MigrationDesc(ctypes.Structure):
 
 class Profile(ctypes.Structure):
     _fields_ = [("ms", ctypes.c_double * 8), ("launches", ctypes.c_longlong * 8), ("substeps", ctypes.c_longlong),
-                ("fallback_particles", ctypes.c_longlong), ("rebin_interval", ctypes.c_longlong)]
+                ("fallback_particles", ctypes.c_longlong), ("rebin_interval", ctypes.c_longlong),
+                ("fused_substeps", ctypes.c_longlong)]
 
 
 PHASES = ("clear", "p2g", "grid", "g2p", "bin", "halo", "migrate")
@@ -263,6 +266,7 @@ class Engine:
         out["substeps"] = pr.substeps
         out["fallback_particles"] = pr.fallback_particles
         out["rebin_interval"] = pr.rebin_interval
+        out["fused_substeps"] = pr.fused_substeps
         return out
 
     def grid_shape(self):

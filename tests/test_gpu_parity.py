@@ -12,7 +12,7 @@ import pytest
 
 import mpm_flip98a_b200 as mpm
 from mpm_flip98a_b200 import scenes
-from mpm_flip98a_b200.engine import FLAG_CAPTURE_POST_P2G, FLAG_NAIVE, FLAG_STRICT
+from mpm_flip98a_b200.engine import FLAG_CAPTURE_POST_P2G, FLAG_G2P_TILE, FLAG_NAIVE, FLAG_NO_FUSE, FLAG_STRICT
 from oracle.cpu import make_params
 from tests.util import bits, fields, rel_l2
 
@@ -20,7 +20,9 @@ pytestmark = pytest.mark.gpu
 
 TOL_STEP = 1e-5   # north_star: single substep, relative L2
 TOL_BULK = 1e-3   # north_star: 1000 substeps, bulk diagnostics
-MODES = [FLAG_NAIVE, 0, FLAG_STRICT]  # per-particle REDs | binned fast (default) | binned, reference association
+# kernel paths: per-particle REDs (exact association) | default: binned, fused G2P->P2G, fast forms |
+# binned unfused | binned fused with the reference's exact association | binned unfused, smem-tile G2P
+MODES = [FLAG_NAIVE, 0, FLAG_NO_FUSE, FLAG_STRICT, FLAG_STRICT | FLAG_G2P_TILE]
 
 
 def engine_for(p0, dim, n_grid, dt, vol_p, alpha=0.0, flags=0, **kw):
