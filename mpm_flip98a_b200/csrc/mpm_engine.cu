@@ -79,7 +79,7 @@ struct mpm_handle {
   bool multi = false;
   MigPtrs mig = {nullptr, nullptr, nullptr, 0, 0};
   float *mig_recv_lo = nullptr, *mig_recv_hi = nullptr;
-  float4 *halo_recv_lo = nullptr, *halo_recv_hi = nullptr;
+  float4 *halo_recv_lo = nullptr, *halo_recv_hi = nullptr, *halo_send_lo = nullptr, *halo_send_hi = nullptr;
   int *mig_count_host = nullptr;  // pinned, 2 ints
   long long mig_sent[2] = {0, 0};
   bool mig_counts_valid = false;
@@ -168,7 +168,6 @@ struct mpm_handle {
   int substep(float dt, int n_steps);
   int step_p2g(float dt);
   int step_grid_g2p(float dt);
-  int step_fused(float dt);
   int read_grid(int stage, float *out);
   int bin_particles(int *cell, int *key, int *order, int *bin_start_out);
   int poll_status();
@@ -310,14 +309,16 @@ int mpm_handle::init() {
     if ((rc = dalloc(&mig.send_lo, words)) || (rc = dalloc(&mig.send_hi, words)) || (rc = dalloc(&mig_recv_lo, words)) ||
         (rc = dalloc(&mig_recv_hi, words)) || (rc = dalloc(&mig.count, 4)))
       return rc;
-    if ((rc = dalloc(&halo_recv_lo, (size_t)halo_nodes())) || (rc = dalloc(&halo_recv_hi, (size_t)halo_nodes()))) return rc;
+    if ((rc = dalloc(&halo_recv_lo, (size_t)halo_nodes())) || (rc = dalloc(&halo_recv_hi, (size_t)halo_nodes())) ||
+        (rc = dalloc(&halo_send_lo, (size_t)halo_nodes())) || (rc = dalloc(&halo_send_hi, (size_t)halo_nodes())))
+      return rc;
     MPM_CUDA(cudaMemsetAsync(mig.count, 0, 16, stream));
     MPM_CUDA(cudaHostAlloc((void **)&mig_count_host, 16, cudaHostAllocDefault));
     mig_count_host[0] = mig_count_host[1] = 0;
   }
   binned = !(cfg.flags & MPM_FLAG_NAIVE) && (D == 2 ? p2g_cells_supported<2>(G) : p2g_cells_supported<3>(G));
   // 2D only: in 3D the Jacobi-SVD-heavy kernels are compute-bound and fusing them costs occupancy (measured slower)
-  fused = binned && !multi && D == 2 && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE));
+  fused = binned && D == 2 && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE));
   if (fused)
     if ((rc = dalloc(&grid_next, (size_t)nodes))) return rc;
 
@@ -363,6 +364,7 @@ int mpm_handle::upload(const void *aos, const int *ids, long long count, int on_
   n = count;
   live = count;
   p2g_ready = false;
+  grid_read = grid;
   tap_valid = false;
   mig_counts_valid = false;
   int rc = rebin_storage();
@@ -431,29 +433,45 @@ int mpm_handle::read(void *aos_out, long long count, int to_device) {
   return MPM_OK;
 }
 
+// Phase 1 of a substep: grid reset + P2G (:50-102).  On the fused schedule the grid usually already holds
+// this P2G (the previous substep's fused kernel produced it) and nothing is launched.
 int mpm_handle::step_p2g(float dt) {
-  p2g_ready = false;
-  grid_read = grid;
-  {
-    Phase ph(this, MPM_PHASE_CLEAR, 0);
-    MPM_CUDA(cudaMemsetAsync(grid, 0, (size_t)nodes * sizeof(float4), stream));  // :50
-  }
-  Phase ph(this, MPM_PHASE_P2G, n > 0 ? 1 : 0);
   const bool strict = (cfg.flags & MPM_FLAG_STRICT) != 0;
-  if (binned) {
-    if (D == 2) launch_p2g_cells<2>(P, G, dt, s2[cur], n_binned, bin_start, gp<2>(), status_dev, stats_dev, strict, stream);
-    else launch_p2g_cells<3>(P, G, dt, s3[cur], n_binned, bin_start, gp<3>(), status_dev, stats_dev, strict, stream);
-    // immigrants since the last re-sort sit behind the binned range: per-particle scatter
-    if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), status_dev, stream);
-    else launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), status_dev, stream);
-  } else {
-    if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), status_dev, stream);
-    else launch_p2g_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), status_dev, stream);
+  if (!(fused && p2g_ready && p2g_dt == dt)) {
+    {
+      Phase ph(this, MPM_PHASE_CLEAR, 0);
+      MPM_CUDA(cudaMemsetAsync(grid, 0, (size_t)nodes * sizeof(float4), stream));  // :50
+    }
+    Phase ph(this, MPM_PHASE_P2G, n > 0 ? 1 : 0);
+    if (binned) {
+      if (D == 2) launch_p2g_cells<2>(P, G, dt, s2[cur], n_binned, bin_start, gp<2>(), status_dev, stats_dev, strict, stream);
+      else launch_p2g_cells<3>(P, G, dt, s3[cur], n_binned, bin_start, gp<3>(), status_dev, stats_dev, strict, stream);
+      // immigrants since the last re-sort sit behind the binned range: per-particle scatter
+      if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), status_dev, stream);
+      else launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), status_dev, stream);
+    } else {
+      if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), status_dev, stream);
+      else launch_p2g_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), status_dev, stream);
+    }
+  }
+  p2g_ready = true;  // `grid` holds P2G(dt) of the current particle state
+  p2g_dt = dt;
+  grid_read = grid;
+  if (multi) {  // the two node columns shared with each neighbour, staged at fixed addresses
+    const size_t hb = (size_t)halo_nodes() * sizeof(float4);
+    MPM_CUDA(cudaMemcpyAsync(halo_send_lo, grid, hb, cudaMemcpyDeviceToDevice, stream));
+    MPM_CUDA(cudaMemcpyAsync(halo_send_hi, grid + (nodes - halo_nodes()), hb, cudaMemcpyDeviceToDevice, stream));
   }
   return MPM_OK;
 }
 
+// Phases 2+3: grid update (:105-131) and G2P (:134-179).  Fused schedule: G2P runs in one kernel with the
+// P2G of the NEXT substep, which lands in the other grid buffer; the buffers then swap.
 int mpm_handle::step_grid_g2p(float dt) {
+  if (!p2g_ready) {
+    err = "step_grid_g2p: no P2G on the grid (call mpm_step_p2g first)";
+    return MPM_E_STATE;
+  }
   if (grid_tap) {
     MPM_CUDA(cudaMemcpyAsync(grid_tap, grid, (size_t)nodes * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
     tap_valid = true;
@@ -463,66 +481,54 @@ int mpm_handle::step_grid_g2p(float dt) {
     if (D == 2) launch_grid_update<2>(P, dt, gp<2>(), stream);
     else launch_grid_update<3>(P, dt, gp<3>(), stream);
   }
-  {
+  // exact association everywhere under MPM_FLAG_STRICT and on the naive path (the bit-faithful modes)
+  const bool strict = (cfg.flags & (MPM_FLAG_STRICT | MPM_FLAG_NAIVE)) != 0;
+  if (multi) MPM_CUDA(cudaMemsetAsync(mig.count, 0, 8, stream));
+  if (fused) {
+    {
+      Phase ph(this, MPM_PHASE_CLEAR, 0);
+      MPM_CUDA(cudaMemsetAsync(grid_next, 0, (size_t)nodes * sizeof(float4), stream));  // :50 of the next substep
+    }
     Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
-    if (multi) MPM_CUDA(cudaMemsetAsync(mig.count, 0, 8, stream));
-    // exact association everywhere under MPM_FLAG_STRICT and on the naive path (the bit-faithful modes)
-    const bool strict = (cfg.flags & (MPM_FLAG_STRICT | MPM_FLAG_NAIVE)) != 0;
+    if (D == 2) {
+      launch_g2p2g<2>(P, G, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mig, strict, stream);
+      // immigrants since the last re-sort: G2P, then their share of the next P2G
+      launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
+      GridPtrs<2> gn = gp<2>();
+      gn.g = grid_next;
+      launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gn, status_dev, stream);
+    } else {
+      launch_g2p2g<3>(P, G, dt, dt, s3[cur], n_binned, bin_start, gp<3>(), grid_next, status_dev, stats_dev, mig, strict, stream);
+      launch_g2p_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), mig, status_dev, strict, stream);
+      GridPtrs<3> gn = gp<3>();
+      gn.g = grid_next;
+      launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gn, status_dev, stream);
+    }
+    grid_read = grid;  // the updated grid of this substep stays readable (mpm_read_grid)
+    float4 *t = grid;
+    grid = grid_next;
+    grid_next = t;
+    p2g_ready = true;  // ... up to the immigrants, which mpm_step_immigrate adds
+    p2g_dt = dt;
+    if (prof_on) prof.fused_substeps++;
+  } else {
+    Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
     if (binned && (cfg.flags & MPM_FLAG_G2P_TILE)) {
       if (D == 2) launch_g2p_bins<2>(P, G, dt, s2[cur], n_binned, bin_start, gp<2>(), mig, status_dev, strict, stream);
       else launch_g2p_bins<3>(P, G, dt, s3[cur], n_binned, bin_start, gp<3>(), mig, status_dev, strict, stream);
-      // immigrants since the last re-sort sit behind the binned range
       if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
       else launch_g2p_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), mig, status_dev, strict, stream);
     } else {
       if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), mig, status_dev, strict, stream);
       else launch_g2p_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), mig, status_dev, strict, stream);
     }
-    if (multi) {
-      MPM_CUDA(cudaMemcpyAsync(mig_count_host, mig.count, 8, cudaMemcpyDeviceToHost, stream));
-      mig_counts_valid = true;
-    }
+    p2g_ready = false;
+  }
+  if (multi) {
+    MPM_CUDA(cudaMemcpyAsync(mig_count_host, mig.count, 8, cudaMemcpyDeviceToHost, stream));
+    mig_counts_valid = true;
   }
   if (prof_on) prof.substeps++;
-  return MPM_OK;
-}
-
-// One substep on the fused schedule: [P2G only if the grid does not already hold it] -> grid update ->
-// fused kernel: G2P of this substep + P2G of the next one into the other grid buffer.
-int mpm_handle::step_fused(float dt) {
-  if (!p2g_ready || p2g_dt != dt) {
-    int rc = step_p2g(dt);  // clear + standalone binned P2G into `grid`
-    if (rc) return rc;
-  }
-  if (grid_tap) {
-    MPM_CUDA(cudaMemcpyAsync(grid_tap, grid, (size_t)nodes * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
-    tap_valid = true;
-  }
-  {
-    Phase ph(this, MPM_PHASE_GRID, 1);
-    if (D == 2) launch_grid_update<2>(P, dt, gp<2>(), stream);
-    else launch_grid_update<3>(P, dt, gp<3>(), stream);
-  }
-  {
-    Phase ph(this, MPM_PHASE_CLEAR, 0);
-    MPM_CUDA(cudaMemsetAsync(grid_next, 0, (size_t)nodes * sizeof(float4), stream));  // :50 of the next substep
-  }
-  {
-    Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
-    const bool strict = (cfg.flags & MPM_FLAG_STRICT) != 0;
-    if (D == 2) launch_g2p2g<2>(P, G, dt, dt, s2[cur], n, bin_start, gp<2>(), grid_next, status_dev, stats_dev, strict, stream);
-    else launch_g2p2g<3>(P, G, dt, dt, s3[cur], n, bin_start, gp<3>(), grid_next, status_dev, stats_dev, strict, stream);
-  }
-  grid_read = grid;  // the updated grid of this substep
-  float4 *t = grid;
-  grid = grid_next;
-  grid_next = t;
-  p2g_ready = true;
-  p2g_dt = dt;
-  if (prof_on) {
-    prof.substeps++;
-    prof.fused_substeps++;
-  }
   return MPM_OK;
 }
 
@@ -542,12 +548,8 @@ int mpm_handle::substep(float dt, int n_steps) {
     const int every = current_interval();
     if (every > 0 && steps_since_sort >= every)
       if ((rc = rebin_storage())) return rc;
-    if (fused) {
-      if ((rc = step_fused(dt))) return rc;
-    } else {
-      if ((rc = step_p2g(dt))) return rc;
-      if ((rc = step_grid_g2p(dt))) return rc;
-    }
+    if ((rc = step_p2g(dt))) return rc;
+    if ((rc = step_grid_g2p(dt))) return rc;
     steps_since_sort++;
   }
   MPM_CUDA(cudaGetLastError());
@@ -711,6 +713,11 @@ int mpm_handle::immigrate(long long n_lo, long long n_hi) {
     launch_immigrate<3>(mig_recv_lo, n_lo, s3[cur], n, stream);
     launch_immigrate<3>(mig_recv_hi, n_hi, s3[cur], n + n_lo, stream);
   }
+  if (fused && p2g_ready && n_lo + n_hi > 0) {
+    // the grid already holds the next substep's P2G of everyone else: add the arrivals' share
+    if (D == 2) launch_p2g_naive<2>(P, p2g_dt, s2[cur], n, n + n_lo + n_hi, gp<2>(), status_dev, stream);
+    else launch_p2g_naive<3>(P, p2g_dt, s3[cur], n, n + n_lo + n_hi, gp<3>(), status_dev, stream);
+  }
   n += n_lo + n_hi;
   live += n_lo + n_hi;
   mig_sent[0] = mig_sent[1] = 0;
@@ -854,8 +861,8 @@ int mpm_halo_describe(mpm_handle *h, mpm_halo_desc *d) {
   memset(d, 0, sizeof *d);
   if (!h->multi) return MPM_OK;
   const long long hn = h->halo_nodes();
-  d->send_lo = h->grid;
-  d->send_hi = h->grid + (h->nodes - hn);
+  d->send_lo = h->halo_send_lo;
+  d->send_hi = h->halo_send_hi;
   d->recv_lo = h->halo_recv_lo;
   d->recv_hi = h->halo_recv_hi;
   d->bytes = hn * (long long)sizeof(float4);

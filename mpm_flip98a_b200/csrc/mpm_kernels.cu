@@ -98,6 +98,48 @@ template void launch_p2g_naive<3>(const Params &, float, const SoA<3> &, long lo
 // One particle of G2P (:134-179).  `fetch(a, b, c, base, gv, vo)` delivers node velocity (and, for FLIP,
 // its pre-gravity value) of stencil offset (a,b,c): straight from L2/L1 (naive kernel) or from the
 // shared-memory tile of the particle's bin (binned kernel).
+// x-slab runs: a particle whose NEW base cell (what the next P2G will use, :55) left [slab_lo, slab_hi) is
+// packed (record + id) into the send buffer of that side and its slot marked dead.  Returns true if it left.
+template <int D>
+__device__ __forceinline__ bool emigrate(const Params &P, const SoA<D> &s, long long i, PState<D> &p, const MigPtrs &mig,
+                                         int *__restrict__ status) {
+  int bx = base_coord(p.x[0], P.inv_dx);
+  bx = max(0, min(bx, P.n_grid - 2));
+  const int side = bx < P.slab_lo ? 0 : (bx >= P.slab_hi ? 1 : -1);
+  if (side < 0) return false;
+  int slot = atomicAdd(&mig.count[side], 1);
+  if (slot >= mig.cap) {
+    atomicOr(status, STATUS_MIGRATION_OVERFLOW);  // stays here (and will be flagged out of slab)
+    return false;
+  }
+  constexpr int W = MigRec<D>::WORDS;
+  float *r = (side == 0 ? mig.send_lo : mig.send_hi) + (size_t)slot * W;
+  float rec[W];
+#pragma unroll
+  for (int c = 0; c < D; c++) {
+    rec[c] = p.x[c];
+    rec[D + c] = p.v[c];
+  }
+#pragma unroll
+  for (int c = 0; c < D; c++)
+#pragma unroll
+    for (int k = 0; k < D; k++) {
+      rec[2 * D + c * D + k] = p.F.d[c][k];
+      rec[2 * D + D * D + c * D + k] = p.C.d[c][k];
+    }
+  rec[2 * D + 2 * D * D] = p.Jp;
+  rec[2 * D + 2 * D * D + 1] = __int_as_float(p.mat);
+  rec[W - 2] = __int_as_float(s.id[i]);
+  rec[W - 1] = 0.0f;
+#pragma unroll
+  for (int k = 0; k < W / 4; k++)
+    reinterpret_cast<float4 *>(r)[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+  p.mat = DEAD;
+  mark_dead(s, i);
+  store_state(s, i, p);  // 3D keeps the material id (now DEAD) in vm.w
+  return true;
+}
+
 // loads particle i, gathers from the grid and returns the NEW state in p (nothing stored yet)
 template <int D, bool FAST, typename Fetch>
 __device__ __forceinline__ void g2p_update(const Params &P, float dt, const SoA<D> &s, long long i, const Fetch &fetch,
@@ -137,43 +179,7 @@ __device__ __forceinline__ void g2p_one(const Params &P, float dt, const SoA<D> 
   g2p_update<D, FAST>(P, dt, s, i, fetch, p);
   const bool dead = MIG && p.mat == DEAD;  // predicate after the loads were issued, not an early exit
   if (dead) return;
-  if (MIG) {
-    // x-slab ownership follows the base cell of the NEW position (what the next P2G will use, :55)
-    int bx = base_coord(p.x[0], P.inv_dx);
-    bx = max(0, min(bx, P.n_grid - 2));
-    const int side = bx < P.slab_lo ? 0 : (bx >= P.slab_hi ? 1 : -1);
-    if (side >= 0) {
-      int slot = atomicAdd(&mig.count[side], 1);
-      if (slot < mig.cap) {
-        constexpr int W = MigRec<D>::WORDS;
-        float *r = (side == 0 ? mig.send_lo : mig.send_hi) + (size_t)slot * W;
-        float rec[W];
-#pragma unroll
-        for (int c = 0; c < D; c++) {
-          rec[c] = p.x[c];
-          rec[D + c] = p.v[c];
-        }
-#pragma unroll
-        for (int c = 0; c < D; c++)
-#pragma unroll
-          for (int k = 0; k < D; k++) {
-            rec[2 * D + c * D + k] = p.F.d[c][k];
-            rec[2 * D + D * D + c * D + k] = p.C.d[c][k];
-          }
-        rec[2 * D + 2 * D * D] = p.Jp;
-        rec[2 * D + 2 * D * D + 1] = __int_as_float(p.mat);
-        rec[W - 2] = __int_as_float(s.id[i]);
-        rec[W - 1] = 0.0f;
-#pragma unroll
-        for (int k = 0; k < W / 4; k++)
-          reinterpret_cast<float4 *>(r)[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
-        p.mat = DEAD;
-        mark_dead(s, i);
-      } else {
-        atomicOr(status, STATUS_MIGRATION_OVERFLOW);  // stays here (and will be flagged out of slab)
-      }
-    }
-  }
+  if (MIG && emigrate<D>(P, s, i, p, mig, status)) return;
   store_state(s, i, p);
 }
 
@@ -286,7 +292,7 @@ template <int D, int B, int NT, int CAP, int TPC, bool FAST, bool MIG, bool FUSE
 __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : MPM_P2G_MINB)
     k_p2g_cells(Params P, BinGeom G, float dt, SoA<D> s, const int *__restrict__ bin_start, float4 *__restrict__ grid,
                 int *__restrict__ status, unsigned long long *__restrict__ stats, const float4 *__restrict__ grid_in,
-                const void *__restrict__ vold_in, float dt_g2p) {
+                const void *__restrict__ vold_in, float dt_g2p, MigPtrs mig) {
   constexpr int M = 1, L = B + 2 * M;
   constexpr int NC = D == 2 ? L * L : L * L * L;
   __shared__ CellRec<D> rec[CAP];
@@ -320,11 +326,17 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : MPM_P2G_MINB)
       if (FUSED) {
         GlobalFetch<D> fetch{grid_in, vold_in};
         g2p_update<D, FAST>(P, dt_g2p, s, (long long)c0 + i, fetch, p);  // :134-179 of this substep
-        store_state(s, (long long)c0 + i, p);
+        if (MIG) {
+          // dead slot: nothing to store; leaving the slab: packed for the neighbour, no P2G here (the
+          // receiving handle scatters it when it arrives)
+          if (p.mat != DEAD && !emigrate<D>(P, s, (long long)c0 + i, p, mig, status)) store_state(s, (long long)c0 + i, p);
+        } else {
+          store_state(s, (long long)c0 + i, p);
+        }
       } else {
         load_full(s, (long long)c0 + i, p);
       }
-      if (MIG && p.mat == DEAD) {  // x-slab runs only: emigrated since the last re-sort
+      if (MIG && p.mat == DEAD) {  // x-slab runs only: emigrated (now or since the last re-sort)
         cell_of[i] = 0xffffu;
         continue;
       }
@@ -539,13 +551,13 @@ template bool p2g_cells_supported<3>(const BinGeom &);
 template <int D, bool FAST, bool MIG, bool FUSED>
 static void launch_cells_variant(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, const int *bin_start,
                                  float4 *grid, int *status, unsigned long long *stats, const float4 *grid_in,
-                                 const void *vold_in, float dt_g2p, cudaStream_t st) {
+                                 const void *vold_in, float dt_g2p, MigPtrs mig, cudaStream_t st) {
   if constexpr (D == 2)
     k_p2g_cells<2, 8, 128, 768, 1, FAST, MIG, FUSED><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, grid, status, stats,
-                                                                            grid_in, vold_in, dt_g2p);
+                                                                            grid_in, vold_in, dt_g2p, mig);
   else
     k_p2g_cells<3, 4, 128, 512, 3, FAST, MIG, FUSED><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, grid, status, stats,
-                                                                            grid_in, vold_in, dt_g2p);
+                                                                            grid_in, vold_in, dt_g2p, mig);
 }
 
 template <int D>
@@ -553,11 +565,11 @@ void launch_p2g_cells(const Params &P, const BinGeom &G, float dt, const SoA<D> 
                       GridPtrs<D> g, int *status, unsigned long long *stats, bool strict, cudaStream_t st) {
   if (n <= 0) return;
   if (strict) {
-    if (P.multi) launch_cells_variant<D, false, true, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, st);
-    else launch_cells_variant<D, false, false, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, st);
+    if (P.multi) launch_cells_variant<D, false, true, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0}, st);
+    else launch_cells_variant<D, false, false, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0}, st);
   } else {
-    if (P.multi) launch_cells_variant<D, true, true, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, st);
-    else launch_cells_variant<D, true, false, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, st);
+    if (P.multi) launch_cells_variant<D, true, true, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0}, st);
+    else launch_cells_variant<D, true, false, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0}, st);
   }
 }
 template void launch_p2g_cells<2>(const Params &, const BinGeom &, float, const SoA<2> &, long long, const int *,
@@ -565,19 +577,27 @@ template void launch_p2g_cells<2>(const Params &, const BinGeom &, float, const 
 template void launch_p2g_cells<3>(const Params &, const BinGeom &, float, const SoA<3> &, long long, const int *,
                                   GridPtrs<3>, int *, unsigned long long *, bool, cudaStream_t);
 
-// fused G2P(dt_g2p, reading g_in) + P2G(dt_p2g, scattering into grid_out); single-GPU handles only
+// fused G2P(dt_g2p, reading g_in) + P2G(dt_p2g, scattering into grid_out)
 template <int D>
 void launch_g2p2g(const Params &P, const BinGeom &G, float dt_g2p, float dt_p2g, const SoA<D> &s, long long n,
                   const int *bin_start, GridPtrs<D> g_in, float4 *grid_out, int *status, unsigned long long *stats,
-                  bool strict, cudaStream_t st) {
+                  MigPtrs mig, bool strict, cudaStream_t st) {
   if (n <= 0) return;
-  if (strict) launch_cells_variant<D, false, false, true>(P, G, dt_p2g, s, bin_start, grid_out, status, stats, g_in.g, g_in.vold, dt_g2p, st);
-  else launch_cells_variant<D, true, false, true>(P, G, dt_p2g, s, bin_start, grid_out, status, stats, g_in.g, g_in.vold, dt_g2p, st);
+#define MPM_FUSED(FAST_, MIG_) \
+  launch_cells_variant<D, FAST_, MIG_, true>(P, G, dt_p2g, s, bin_start, grid_out, status, stats, g_in.g, g_in.vold, dt_g2p, mig, st)
+  if (strict) {
+    if (mig.enabled) MPM_FUSED(false, true);
+    else MPM_FUSED(false, false);
+  } else {
+    if (mig.enabled) MPM_FUSED(true, true);
+    else MPM_FUSED(true, false);
+  }
+#undef MPM_FUSED
 }
 template void launch_g2p2g<2>(const Params &, const BinGeom &, float, float, const SoA<2> &, long long, const int *,
-                              GridPtrs<2>, float4 *, int *, unsigned long long *, bool, cudaStream_t);
+                              GridPtrs<2>, float4 *, int *, unsigned long long *, MigPtrs, bool, cudaStream_t);
 template void launch_g2p2g<3>(const Params &, const BinGeom &, float, float, const SoA<3> &, long long, const int *,
-                              GridPtrs<3>, float4 *, int *, unsigned long long *, bool, cudaStream_t);
+                              GridPtrs<3>, float4 *, int *, unsigned long long *, MigPtrs, bool, cudaStream_t);
 
 // ------------------------------------------------------------------------------------------------
 // naive G2P: one thread per particle, 3^D node reads through the read-only path, in-place update.

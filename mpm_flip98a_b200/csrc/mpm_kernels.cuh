@@ -41,7 +41,7 @@ void launch_p2g_cells(const Params &P, const BinGeom &G, float dt, const SoA<D> 
 template <int D>
 void launch_g2p2g(const Params &P, const BinGeom &G, float dt_g2p, float dt_p2g, const SoA<D> &s, long long n,
                   const int *bin_start, GridPtrs<D> g_in, float4 *grid_out, int *status, unsigned long long *stats,
-                  bool strict, cudaStream_t st);
+                  MigPtrs mig, bool strict, cudaStream_t st);
 template <int D>
 void launch_g2p_bins(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, long long n, const int *bin_start,
                      GridPtrs<D> g, MigPtrs mig, int *status, bool strict, cudaStream_t st);

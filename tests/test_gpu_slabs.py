@@ -7,7 +7,7 @@ import pytest
 
 import mpm_flip98a_b200 as mpm
 from mpm_flip98a_b200 import parallel, scenes
-from mpm_flip98a_b200.engine import FLAG_NAIVE
+from mpm_flip98a_b200.engine import FLAG_NAIVE, FLAG_NO_FUSE
 from oracle.cpu import make_params
 from tests.util import bits, fields, rel_l2
 
@@ -26,7 +26,7 @@ def run_slabs(p, dim, n_grid, world, steps, dt, vol_p, alpha=0.0, flags=0, rebin
     return out, status, counts, slabs
 
 
-@pytest.mark.parametrize("flags", [FLAG_NAIVE, 0])
+@pytest.mark.parametrize("flags", [FLAG_NAIVE, 0, FLAG_NO_FUSE])
 @pytest.mark.parametrize("world", [2, 3, 4])
 def test_one_warm_substep_matches_oracle(oracle, shipped, world, flags):
     p = shipped["step1000"]  # spread over x in [0.05, 0.97]: every slab owns particles
@@ -40,7 +40,7 @@ def test_one_warm_substep_matches_oracle(oracle, shipped, world, flags):
     assert np.array_equal(bits(got[:, -1]), bits(p[:, -1]))
 
 
-@pytest.mark.parametrize("flags", [FLAG_NAIVE, 0])
+@pytest.mark.parametrize("flags", [FLAG_NAIVE, 0, FLAG_NO_FUSE])
 def test_3d_slabs_one_warm_substep(oracle, flags):
     n = 32
     dt, vol = scenes.scaled_constants(n)
@@ -56,7 +56,7 @@ def test_3d_slabs_one_warm_substep(oracle, flags):
         assert rel_l2(fg[k], fw[k]) <= 1e-5, (k, rel_l2(fg[k], fw[k]))
 
 
-@pytest.mark.parametrize("flags", [FLAG_NAIVE, 0])
+@pytest.mark.parametrize("flags", [FLAG_NAIVE, 0, FLAG_NO_FUSE])
 def test_migration_conserves_particles_and_tracks_the_single_handle_run(oracle, flags):
     # jelly block thrown sideways across three slab cuts: well-conditioned, so slabs vs one handle
     # vs the CPU oracle must agree closely even after hundreds of substeps
