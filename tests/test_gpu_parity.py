@@ -250,3 +250,43 @@ def test_large_scale_properties():
     assert np.isfinite(out).all()
     assert np.array_equal(bits(out[:, -1]), bits(p[:, -1]))
     assert out[:, 3].mean() < 0  # it falls
+
+
+@pytest.mark.parametrize("flags", MODES)
+def test_changing_dt_between_calls(oracle, flags):
+    # the fused schedule pre-computes the next substep's P2G with the current dt: a different dt on the
+    # next call must invalidate it (results = the oracle's sequence of the same dts)
+    p = scenes.jelly_drop()
+    P = make_params()
+    oracle.advance(P, 1e-4, p, 450)  # warm: in contact with the floor
+    want = p.copy()
+    for dt, k in ((1e-4, 3), (5e-5, 2), (1e-4, 1), (2.5e-5, 4)):
+        oracle.advance(P, dt, want, k)
+    with engine_for(p, 2, 80, 1e-4, 1.0, 0.0, flags) as e:
+        for dt, k in ((1e-4, 3), (5e-5, 2), (1e-4, 1), (2.5e-5, 4)):
+            e.substep(k, dt=dt)
+        got = e.read()
+        assert e.poll_status() == 0
+    fw, fg = fields(want, 2), fields(got, 2)
+    for k in fw:
+        assert rel_l2(fg[k], fw[k]) <= 2e-5, (k, rel_l2(fg[k], fw[k]))  # 10 substeps of <= 1e-5 noise each, not additive
+
+
+@pytest.mark.parametrize("flags", [FLAG_NAIVE, 0])
+def test_3d_many_substeps_bulk(oracle, flags):
+    # 3D lift over 300 substeps on a well-conditioned scene (elastic slab settling): bulk diagnostics vs the oracle
+    n = 32
+    dt, vol = scenes.scaled_constants(n)
+    p = scenes.collapse_3d(n, per_side=2, y_top=0.3, xz=(0.25, 0.75))
+    p[:, -1] = np.full(len(p), scenes.JELLY, np.int32).view(np.float32)
+    P = make_params(dim=3, n_grid=n, vol_p=vol)
+    want = p.copy()
+    oracle.advance(P, dt, want, 300)
+    with engine_for(p, 3, n, dt, vol, 0.0, flags) as e:
+        e.substep(300)
+        got = e.read()
+        assert e.poll_status() == 0
+    bw, bg = scenes.bulk(want, 3), scenes.bulk(got, 3)
+    assert np.abs(bw["com"] - bg["com"]).max() <= 1e-3 * np.abs(bw["com"]).max()
+    assert abs(bw["ke"] - bg["ke"]) <= 1e-3 * bw["ke"]
+    assert rel_l2(got[:, 0:3], want[:, 0:3]) <= 1e-3
