@@ -216,7 +216,8 @@ MPM_HD void svd3(const Mat<3> &A_in, Mat<3> &U, float sig[3], Mat<3> &V) {
       float a = A.d[p][0] * A.d[p][0] + A.d[p][1] * A.d[p][1] + A.d[p][2] * A.d[p][2];
       float b = A.d[q][0] * A.d[q][0] + A.d[q][1] * A.d[q][1] + A.d[q][2] * A.d[q][2];
       float c = A.d[p][0] * A.d[q][0] + A.d[p][1] * A.d[q][1] + A.d[p][2] * A.d[q][2];
-      if (fabsf(c) <= 1e-12f * sqrtf(a * b)) continue;
+      // converged pair: the columns are orthogonal to fp32 resolution (|cos| <= 2 ulp); later sweeps then only pay the test
+      if (fabsf(c) <= 2.4e-7f * sqrtf(a * b)) continue;
       float zeta = (b - a) / (2.0f * c);
       float t = (zeta >= 0.0f ? 1.0f : -1.0f) / (fabsf(zeta) + sqrtf(1.0f + zeta * zeta));
       float cs = 1.0f / sqrtf(1.0f + t * t);

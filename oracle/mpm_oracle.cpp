@@ -448,7 +448,8 @@ inline void svd3(const M3 &A_in, M3 &U, float sig[3], M3 &V) {
       float a = A.d[p][0] * A.d[p][0] + A.d[p][1] * A.d[p][1] + A.d[p][2] * A.d[p][2];
       float b = A.d[q][0] * A.d[q][0] + A.d[q][1] * A.d[q][1] + A.d[q][2] * A.d[q][2];
       float c = A.d[p][0] * A.d[q][0] + A.d[p][1] * A.d[q][1] + A.d[p][2] * A.d[q][2];
-      if (std::abs(c) <= 1e-12f * std::sqrt(a * b)) continue;
+      // converged pair: the columns are orthogonal to fp32 resolution (|cos| <= 2 ulp); later sweeps then only pay the test
+      if (std::abs(c) <= 2.4e-7f * std::sqrt(a * b)) continue;
       float zeta = (b - a) / (2.0f * c);
       float t = (zeta >= 0.0f ? 1.0f : -1.0f) / (std::abs(zeta) + std::sqrt(1.0f + zeta * zeta));
       float cs = 1.0f / std::sqrt(1.0f + t * t);
