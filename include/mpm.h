@@ -88,7 +88,7 @@ typedef struct mpm_config {
   void *stream;       /* cudaStream_t to launch on; NULL = a stream owned by the handle */
   int bin_edge;       /* cells per bin edge for the block binning; 0 = engine default */
   int rebin_every;    /* re-sort the particle storage by bin every this many substeps; <0 = never;
-                         0 = engine default: 32 on the naive path, adaptive 4..128 on the binned path
+                         0 = engine default: 32 on the naive path, adaptive 4..512 on the binned path
                          (doubled while < 0.1% of particle-steps outrun the 1-cell bin margin) */
   int reserved[6];
 } mpm_config;
@@ -132,6 +132,8 @@ int mpm_upload_particles_ids(mpm_handle *h, const void *aos, const int *ids, lon
 long long mpm_read_particles_ids(mpm_handle *h, void *aos_out, int *ids_out, long long max_n, int to_device);
 long long mpm_storage_extent(const mpm_handle *h);
 long long mpm_particle_count(const mpm_handle *h);
+/* Re-sorts the particle storage by bin now (the engine does it on its own every rebin interval). */
+int mpm_resort(mpm_handle *h);
 int mpm_synchronize(mpm_handle *h);
 /* Sticky device-side status (MPM_E_DOMAIN / MPM_E_CFL) accumulated since the last call; synchronises. */
 int mpm_poll_status(mpm_handle *h);

@@ -54,8 +54,8 @@ struct mpm_handle {
 
   int *status_dev = nullptr;
   unsigned long long *stats_dev = nullptr;  // [0] = binned-P2G fallback particles (total), [1] = since the last re-sort
-  // adaptive re-sort interval (binned path, cfg.rebin_every == 0): doubled while almost no particle
-  // outruns the 1-cell bin margin between re-sorts, halved when more than 1% do
+  // adaptive re-sort interval (binned path, cfg.rebin_every == 0): doubled (up to 512) while almost no
+  // particle outruns the 1-cell bin margin between re-sorts, halved (down to 4) when more than 1% do
   int rebin_interval = 16;
   unsigned long long *stats_host = nullptr;  // pinned copy of stats_dev taken at each re-sort
   cudaEvent_t stats_ev = nullptr;
@@ -379,7 +379,7 @@ int mpm_handle::rebin_storage() {
     // how many particle-steps of the interval that just ended took the fallback path?
     if (stats_pending && cudaEventQuery(stats_ev) == cudaSuccess) {
       const double frac = stats_particle_steps > 0 ? (double)stats_host[1] / (double)stats_particle_steps : 0.0;
-      if (frac < 1e-3 && rebin_interval < 128) rebin_interval *= 2;
+      if (frac < 1e-3 && rebin_interval < 512) rebin_interval *= 2;
       else if (frac > 1e-2 && rebin_interval > 4) rebin_interval /= 2;
       stats_pending = false;
     }
@@ -814,6 +814,11 @@ int mpm_read_particles(mpm_handle *h, void *aos_out, long long n, int to_device)
 }
 int mpm_read_grid(mpm_handle *h, int stage, float *out) { return h ? h->read_grid(stage, out) : MPM_E_INVALID; }
 long long mpm_particle_count(const mpm_handle *h) { return h ? h->live : -1; }
+int mpm_resort(mpm_handle *h) {
+  if (!h) return MPM_E_INVALID;
+  cudaSetDevice(h->cfg.device);
+  return h->rebin_storage();
+}
 int mpm_synchronize(mpm_handle *h) {
   if (!h) return MPM_E_INVALID;
   cudaSetDevice(h->cfg.device);

@@ -81,6 +81,7 @@ SYMBOLS = {
     "mpm_read_particles_ids": (ctypes.c_longlong, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int]),
     "mpm_storage_extent": (ctypes.c_longlong, [_H]),
     "mpm_particle_count": (ctypes.c_longlong, [_H]),
+    "mpm_resort": (ctypes.c_int, [_H]),
     "mpm_synchronize": (ctypes.c_int, [_H]),
     "mpm_poll_status": (ctypes.c_int, [_H]),
     "mpm_profile_enable": (ctypes.c_int, [_H, ctypes.c_int]),
@@ -239,6 +240,9 @@ class Engine:
 
     def substep(self, n_steps=1, dt=0.0):
         self._check(self.lib.mpm_substep(self.h, dt, n_steps))
+
+    def resort(self):
+        self._check(self.lib.mpm_resort(self.h))
 
     def synchronize(self):
         self._check(self.lib.mpm_synchronize(self.h))
