@@ -72,6 +72,8 @@ struct mpm_handle {
   BinGeom G;
   SortBuffers sb;
   int *bin_start = nullptr;
+  int *active_bins = nullptr;       // compacted ids of the non-empty bins (refreshed by every re-sort)
+  unsigned *active_offs = nullptr;  // scan scratch, n_bins + 2
   int *cell_dev = nullptr;
   int key_bits = 0;
 
@@ -300,7 +302,11 @@ int mpm_handle::init() {
   for (int b = 0; b < 2; b++)
     if ((rc = dalloc(&sb.key[b], cap)) || (rc = dalloc(&sb.val[b], cap))) return rc;
   if ((rc = dalloc(&sb.hist, sort_hist_elems(cap)))) return rc;
-  if ((rc = dalloc(&sb.scan_tmp, scan_tmp_elems((long long)sort_hist_elems(cap))))) return rc;
+  {  // the scan scratch serves the radix histograms and the active-bin compaction (n_bins + 1 flags)
+    long long longest = (long long)sort_hist_elems(cap);
+    if ((long long)G.n_bins + 2 > longest) longest = (long long)G.n_bins + 2;
+    if ((rc = dalloc(&sb.scan_tmp, scan_tmp_elems(longest)))) return rc;
+  }
   if ((rc = dalloc(&bin_start, (size_t)G.n_bins + 2))) return rc;
   if (multi) {
     mig.cap = (int)(cap / 64 > 4096 ? cap / 64 : 4096);
@@ -316,6 +322,7 @@ int mpm_handle::init() {
     MPM_CUDA(cudaHostAlloc((void **)&mig_count_host, 16, cudaHostAllocDefault));
     mig_count_host[0] = mig_count_host[1] = 0;
   }
+  if ((rc = dalloc(&active_bins, (size_t)G.n_bins + 1)) || (rc = dalloc(&active_offs, (size_t)G.n_bins + 2))) return rc;
   binned = !(cfg.flags & MPM_FLAG_NAIVE) && (D == 2 ? p2g_cells_supported<2>(G) : p2g_cells_supported<3>(G));
   // 2D only: in 3D the Jacobi-SVD-heavy kernels are compute-bound and fusing them costs occupancy (measured slower)
   fused = binned && D == 2 && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE));
@@ -402,6 +409,14 @@ int mpm_handle::rebin_storage() {
   if (D == 2) launch_reorder<2>(s2[cur], s2[cur ^ 1], sb.val[r], n, stream);
   else launch_reorder<3>(s3[cur], s3[cur ^ 1], sb.val[r], n, stream);
   cur ^= 1;
+  if (binned) {  // the CTA-per-bin kernels launch over the non-empty bins only
+    launch_active_bins(bin_start, G.n_bins, active_offs, sb.scan_tmp, active_bins, stream);
+    unsigned n_active = 0;
+    MPM_CUDA(cudaMemcpyAsync(&n_active, active_offs + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
+    MPM_CUDA(cudaStreamSynchronize(stream));
+    G.active = active_bins;
+    G.n_active = (int)n_active;
+  }
   MPM_CUDA(cudaGetLastError());
   if (multi) {  // dead (emigrated) slots sorted behind the last bin: drop them from the storage extent
     int live_extent = 0;

@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
   __shared__ int item_first[NC + 1];              // per cell: index of its first item (exclusive scan)
   __shared__ unsigned short item_cell[MAXI];
   const int tid = threadIdx.x;
-  const int bin = blockIdx.x;
+  const int bin = G.active ? G.active[blockIdx.x] : (int)blockIdx.x;
   const int s0 = bin_start[bin], s1 = bin_start[bin + 1];
   if (s0 >= s1) return;
   // bin coordinates -> origin (global cell index of local cell 0, i.e. bin origin minus the margin)
@@ -562,10 +562,10 @@ static void launch_cells_variant(const Params &P, const BinGeom &G, float dt, co
                                  float4 *grid, int *status, unsigned long long *stats, const float4 *grid_in,
                                  const void *vold_in, float dt_g2p, MigPtrs mig, cudaStream_t st) {
   if constexpr (D == 2)
-    k_p2g_cells<2, 8, 128, 768, 1, FAST, MIG, FUSED><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, grid, status, stats,
+    k_p2g_cells<2, 8, 128, 768, 1, FAST, MIG, FUSED><<<(G.active ? G.n_active : G.n_bins), 128, 0, st>>>(P, G, dt, s, bin_start, grid, status, stats,
                                                                             grid_in, vold_in, dt_g2p, mig);
   else
-    k_p2g_cells<3, 4, 128, 512, 3, FAST, MIG, FUSED><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, grid, status, stats,
+    k_p2g_cells<3, 4, 128, 512, 3, FAST, MIG, FUSED><<<(G.active ? G.n_active : G.n_bins), 128, 0, st>>>(P, G, dt, s, bin_start, grid, status, stats,
                                                                             grid_in, vold_in, dt_g2p, mig);
 }
 
@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(NT) k_g2p_bins(Params P, BinGeom G, float dt, 
   constexpr int T = B + 4, NN = D == 2 ? T * T : T * T * T;
   __shared__ float4 tile[NN];
   __shared__ float4 tile_o[(D == 3 && FLIP) ? NN : 1];
-  const int bin = blockIdx.x;
+  const int bin = G.active ? G.active[blockIdx.x] : (int)blockIdx.x;
   const int s0 = bin_start[bin], s1 = bin_start[bin + 1];
   if (s0 >= s1) return;
   TileFetch<D, B, FLIP> fetch;
@@ -729,8 +729,8 @@ void launch_g2p_bins(const Params &P, const BinGeom &G, float dt, const SoA<D> &
   constexpr int B = D == 2 ? 8 : 4;
 #define MPM_G2P_BINS(FLIP_, MIG_)                                                                                      \
   {                                                                                                                    \
-    if (strict) k_g2p_bins<D, B, 128, FLIP_, MIG_, false><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, g.vold, mig, status); \
-    else k_g2p_bins<D, B, 128, FLIP_, MIG_, true><<<G.n_bins, 128, 0, st>>>(P, G, dt, s, bin_start, g.g, g.vold, mig, status);         \
+    if (strict) k_g2p_bins<D, B, 128, FLIP_, MIG_, false><<<(G.active ? G.n_active : G.n_bins), 128, 0, st>>>(P, G, dt, s, bin_start, g.g, g.vold, mig, status); \
+    else k_g2p_bins<D, B, 128, FLIP_, MIG_, true><<<(G.active ? G.n_active : G.n_bins), 128, 0, st>>>(P, G, dt, s, bin_start, g.g, g.vold, mig, status);         \
   }
   if (flip) {
     if (mig.enabled) MPM_G2P_BINS(true, true)

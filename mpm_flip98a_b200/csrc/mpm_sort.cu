@@ -18,6 +18,8 @@ BinGeom make_bin_geom(const Params &P, int dim, int edge) {
   G.nb[1] = (P.n_grid - 1 + edge - 1) / edge;
   G.nb[2] = dim == 3 ? G.nb[1] : 1;
   G.n_bins = G.nb[0] * G.nb[1] * G.nb[2];
+  G.active = nullptr;
+  G.n_active = 0;
   return G;
 }
 
@@ -228,6 +230,22 @@ __global__ void k_bin_starts(const unsigned *__restrict__ key, long long n, int 
 }
 void launch_bin_starts(const unsigned *sorted_key, long long n, int n_bins, int *bin_start, cudaStream_t st) {
   k_bin_starts<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(sorted_key, n, n_bins, bin_start);
+}
+
+__global__ void k_flag_active(const int *__restrict__ bin_start, int n_bins, unsigned *__restrict__ offs) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= n_bins) offs[b] = (b < n_bins && bin_start[b + 1] > bin_start[b]) ? 1u : 0u;
+}
+__global__ void k_compact_active(const int *__restrict__ bin_start, int n_bins, const unsigned *__restrict__ offs,
+                                 int *__restrict__ active) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n_bins && bin_start[b + 1] > bin_start[b]) active[offs[b]] = b;
+}
+void launch_active_bins(const int *bin_start, int n_bins, unsigned *offs, unsigned *scan_tmp, int *active, cudaStream_t st) {
+  unsigned blocks = (unsigned)((n_bins + 1 + 255) / 256);
+  k_flag_active<<<blocks, 256, 0, st>>>(bin_start, n_bins, offs);
+  exclusive_scan_u32(offs, (long long)n_bins + 1, scan_tmp, st);  // offs[n_bins] = number of active bins
+  k_compact_active<<<blocks, 256, 0, st>>>(bin_start, n_bins, offs, active);
 }
 
 __global__ void k_iota(int *v, long long n) {
