@@ -122,6 +122,36 @@ def cpu_sample(name, max_seconds=20.0):
     return val, desc, (O, P, dt, p)
 
 
+def unmodified_reference_c1(steps=300):
+    """The UNMODIFIED reference translation unit (oracle/_ref, built from /root/reference in the build container)
+    on the only scene it can run -- its own: 80^2 grid, 3000 particles (BASELINE configs[0]).  Information only."""
+    try:
+        from oracle.cpu import Reference
+        if not Reference.available():
+            return None
+        # the reference's logger greets on stdout when its library is loaded (taichi.h:16302): keep stdout for
+        # the one JSON line by pointing fd 1 at stderr while the library loads
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            R = Reference()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+        g = np.load(os.path.join(ROOT, "tests", "golden", "shipped_scene.npz"))
+        R.set(g["step100"].copy())
+        R.advance(20)
+        t0 = time.perf_counter()
+        R.advance(steps)
+        el = time.perf_counter() - t0
+        return {"value": 3000 * steps / el, "unit": "particle-substeps/s", "cores": 1, "kind": "reference",
+                "sample": "shipped scene (80^2 grid, 3000 particles), %d substeps from the golden step-100 state" % steps}
+    except Exception as e:  # never let the information leg break the bench line
+        return {"unavailable": str(e)[:200]}
+
+
 def run_reference(args):
     """Reference arm: the reference's own CPU algorithm for the path (oracle port -- the reference
     translation unit itself only compiles for its fixed 80^2 scene), single thread as shipped."""
@@ -148,7 +178,8 @@ def run_reference(args):
                              "sample": sample},
             "e2e": {"value": value, "unit": "particle-substeps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
-            "host_cores_total": os.cpu_count()}
+            "host_cores_total": os.cpu_count(),
+            "unmodified_reference_c1": unmodified_reference_c1()}
     print(json.dumps(line), flush=True)
 
 
@@ -263,7 +294,8 @@ def main():
     if not args.no_cpu:
         val, desc, _ = cpu_sample(args.workload)
         line["cpu_baseline"] = {"value": val, "unit": "particle-substeps/s", "cores": 1, "kind": "port",
-                                "sample": desc, "host_cores_total": os.cpu_count()}
+                                "sample": desc, "host_cores_total": os.cpu_count(),
+                                "unmodified_reference_c1": unmodified_reference_c1()}
     print(json.dumps(line), flush=True)
 
 

@@ -66,7 +66,6 @@ struct mpm_handle {
     return binned ? rebin_interval : 32;
   }
   bool binned = false;                      // CTA-per-bin P2G (default) vs MPM_FLAG_NAIVE
-  int status_host_sticky = 0;
 
   // binning
   BinGeom G;
@@ -614,12 +613,8 @@ int mpm_handle::bin_particles(int *cell, int *key, int *order, int *bin_start_ou
   if (cell) MPM_CUDA(cudaMemcpyAsync(cell, cell_dev, (size_t)n * D * 4, cudaMemcpyDeviceToHost, stream));
   launch_iota(sb.val[0], n, stream);
   int r = radix_sort_pairs(sb, n, key_bits, stream);
-  // bin starts into the histogram scratch (bin_start itself belongs to the storage order)
-  int *tmp_start = (int *)sb.hist;
-  if ((size_t)G.n_bins + 1 > sort_hist_elems(cap)) {
-    err = "bin_particles: scratch too small";
-    return MPM_E_INVALID;
-  }
+  // bin starts into the active-bin scan scratch (n_bins + 2 words; bin_start itself belongs to the storage order)
+  int *tmp_start = (int *)active_offs;
   if (order) MPM_CUDA(cudaMemcpyAsync(order, sb.val[r], (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
   launch_bin_starts(sb.key[r], n, G.n_bins, tmp_start, stream);
   if (bin_start_out)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Summarise an .ncu-rep (read here, no GPU): python tools_ncu_summary.py gpurun_out/x.ncu-rep [out.md]"""
+"""Summarise an .ncu-rep (read here, no GPU): python profiles/ncu_summary.py gpurun_out/x.ncu-rep [out.md]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
