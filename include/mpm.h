@@ -31,7 +31,7 @@ enum {
   MPM_E_CUDA = -2,      /* CUDA runtime error (text in mpm_last_error) */
   MPM_E_CAPACITY = -3,  /* more particles than the handle was created for */
   MPM_E_DOMAIN = -4,    /* a particle left the grid (the reference has no bounds check, :97,:150) */
-  MPM_E_CFL = -5,       /* a particle crossed more than one bin in a substep */
+  MPM_E_CFL = -5,       /* reserved (the engine tolerates any drift: stale bin membership only costs speed) */
   MPM_E_STATE = -6      /* call sequence error (e.g. read before upload) */
 };
 
@@ -54,9 +54,9 @@ enum {
                                          (no binning); the small-scene / debugging path */
   MPM_FLAG_G2P_TILE = 1 << 3,         /* binned path: G2P stages each bin's node tile in shared memory
                                          (measured no faster than the read-only-path gather: off by default) */
-  MPM_FLAG_NO_FUSE = 1 << 4,          /* keep P2G and G2P as separate kernels (default on one GPU: G2P of a
-                                         substep and P2G of the next run fused, one particle read + one
-                                         write per substep; x-slab handles always run unfused) */
+  MPM_FLAG_NO_FUSE = 1 << 4,          /* keep P2G and G2P as separate kernels (2D default, single GPU and
+                                         x-slabs alike: G2P of a substep and P2G of the next run as ONE
+                                         kernel, one particle read + one write per substep; 3D is unfused) */
   MPM_FLAG_STRICT = 1 << 2            /* binned path: P2G node contributions (:92-100) and the G2P gather
                                          (:153-154) keep the reference's exact association instead of the
                                          separable / hoisted FMA forms (algebraically identical, ~1e-7
@@ -135,7 +135,8 @@ long long mpm_particle_count(const mpm_handle *h);
 /* Re-sorts the particle storage by bin now (the engine does it on its own every rebin interval). */
 int mpm_resort(mpm_handle *h);
 int mpm_synchronize(mpm_handle *h);
-/* Sticky device-side status (MPM_E_DOMAIN / MPM_E_CFL) accumulated since the last call; synchronises. */
+/* Sticky device-side status (MPM_E_DOMAIN, MPM_E_CAPACITY for a migration-buffer overflow) accumulated since
+ * the last call; synchronises. */
 int mpm_poll_status(mpm_handle *h);
 
 /* ---- per-phase device timing (CUDA events on the handle's stream) and launch counts ---------- */
