@@ -190,7 +190,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--warm-substeps", type=int, default=120, help="untimed substeps to reach a warm state")
+    ap.add_argument("--warm-substeps", type=int, default=130,
+                    help="untimed substeps to reach a warm state (the adaptive storage re-sort fires at substeps 16, 32, 64, "
+                         "128, 256, 512: 130 puts a default-length timed region between two of them; the `resort` object "
+                         "of the output reports the re-sort cost and the steady-state rate with it amortised)")
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--naive", action="store_true", help="one-thread-per-particle kernels (MPM_FLAG_NAIVE)")
     ap.add_argument("--no-fuse", action="store_true", help="separate P2G and G2P kernels (MPM_FLAG_NO_FUSE)")
