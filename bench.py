@@ -197,6 +197,8 @@ def main():
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--naive", action="store_true", help="one-thread-per-particle kernels (MPM_FLAG_NAIVE)")
     ap.add_argument("--no-fuse", action="store_true", help="separate P2G and G2P kernels (MPM_FLAG_NO_FUSE)")
+    ap.add_argument("--overlap", action="store_true",
+                    help="N > 1: interior bins on a side stream while the slab boundary is exchanged (MPM_FLAG_OVERLAP)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rebin-every", type=int, default=0, help="storage re-sort interval (0 = engine default)")
     args = ap.parse_args()
@@ -407,7 +409,7 @@ def run_slabs(args, rank, world, local):
     ids_out = torch.empty(int(n_local * 1.1) + 65536, dtype=torch.int32).pin_memory()
 
     stream = torch.cuda.Stream()
-    flags = FLAG_NAIVE if args.naive else 0
+    flags = FLAG_NAIVE if args.naive else (32 if args.overlap else 0)
     cap = int(n_local * 1.1) + 65536
     with torch.cuda.stream(stream):
         eng = mpm.Engine(dim=dim, n_grid=n_grid, capacity=cap, dt=dt, vol_p=vol, alpha=alpha, device=local,
@@ -474,7 +476,8 @@ def run_slabs(args, rank, world, local):
                                                         % (min(b - a for a, b in slabs), max(b - a for a, b in slabs)),
                                        "weak_scaling_rule": "n_grid = 8192*sqrt(N), same fill fractions: particles "
                                                             "and nodes per GPU as at N=1",
-                                       "exchange": "NCCL P2P: 2 ghost node columns each way + emigrant records"})
+                                       "exchange": "NCCL P2P: 2 ghost node columns each way + emigrant records"
+                                                   + (", overlapped with the interior bins" if args.overlap else "")})
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()

@@ -31,7 +31,7 @@ enum {
   MPM_E_CUDA = -2,      /* CUDA runtime error (text in mpm_last_error) */
   MPM_E_CAPACITY = -3,  /* more particles than the handle was created for */
   MPM_E_DOMAIN = -4,    /* a particle left the grid (the reference has no bounds check, :97,:150) */
-  MPM_E_CFL = -5,       /* reserved (the engine tolerates any drift: stale bin membership only costs speed) */
+  MPM_E_CFL = -5,       /* MPM_FLAG_OVERLAP only: a particle of an interior bin reached the slab cut */
   MPM_E_STATE = -6      /* call sequence error (e.g. read before upload) */
 };
 
@@ -57,6 +57,9 @@ enum {
   MPM_FLAG_NO_FUSE = 1 << 4,          /* keep P2G and G2P as separate kernels (2D default, single GPU and
                                          x-slabs alike: G2P of a substep and P2G of the next run as ONE
                                          kernel, one particle read + one write per substep; 3D is unfused) */
+  MPM_FLAG_OVERLAP = 1 << 5,          /* x-slab handles on the fused schedule: bins >= 2 bin columns away from the
+                                         slab cuts run on a side stream while the boundary bins finish first, so
+                                         the caller's migration / halo exchange overlaps the interior compute */
   MPM_FLAG_STRICT = 1 << 2            /* binned path: P2G node contributions (:92-100) and the G2P gather
                                          (:153-154) keep the reference's exact association instead of the
                                          separable / hoisted FMA forms (algebraically identical, ~1e-7
@@ -147,7 +150,7 @@ enum {
   MPM_PHASE_G2P = 3,   /* :134-179 */
   MPM_PHASE_BIN = 4,   /* binning / sort (no counterpart in the reference) */
   MPM_PHASE_HALO = 5,
-  MPM_PHASE_MIGRATE = 6,
+  MPM_PHASE_MIGRATE = 6, /* immigrant unpack; with MPM_FLAG_OVERLAP also the boundary bins' fused kernel */
   MPM_PHASE_COUNT = 8
 };
 typedef struct mpm_profile {

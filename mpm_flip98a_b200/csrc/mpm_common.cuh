@@ -29,6 +29,7 @@ struct MigPtrs {
   int *count;                // device: [0] = lo, [1] = hi
   int cap;
   int enabled;
+  int interior;  // 1: this launch covers bins far from the slab cuts and must not emigrate (checked, flagged)
 };
 template <int D>
 struct MigRec {

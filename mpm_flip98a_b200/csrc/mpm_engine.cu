@@ -47,6 +47,19 @@ struct mpm_handle {
   // `grid`; the two swap each substep.  grid_read = the buffer that holds the last UPDATED grid (mpm_read_grid).
   float4 *grid_next = nullptr, *grid_read = nullptr;
   bool fused = false, p2g_ready = false;
+  // overlapped slab schedule (MPM_FLAG_OVERLAP): the fused kernel of the bins >= 2 bin columns away from the slab
+  // cuts runs on a side stream while the main stream finishes the boundary bins and the caller exchanges
+  // emigrants / halo columns; act_lo_end / act_hi_begin split the (sorted) active-bin list into lo | interior | hi
+  bool overlap = false, side_busy = false;
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_ready = nullptr, ev_side_done = nullptr;
+  int act_lo_end = 0, act_hi_begin = 0;
+  void join_side() {  // everything issued on the main stream after this sees the side stream's work
+    if (side_busy) {
+      cudaStreamWaitEvent(stream, ev_side_done, 0);
+      side_busy = false;
+    }
+  }
   float p2g_dt = 0.0f;
   void *vold = nullptr;
   long long nodes = 0;
@@ -78,7 +91,7 @@ struct mpm_handle {
 
   // x-slab exchange (multi == this handle owns a strict sub-range of base-cell columns)
   bool multi = false;
-  MigPtrs mig = {nullptr, nullptr, nullptr, 0, 0};
+  MigPtrs mig = {nullptr, nullptr, nullptr, 0, 0, 0};
   float *mig_recv_lo = nullptr, *mig_recv_hi = nullptr;
   float4 *halo_recv_lo = nullptr, *halo_recv_hi = nullptr, *halo_send_lo = nullptr, *halo_send_hi = nullptr;
   int *mig_count_host = nullptr;  // pinned, 2 ints
@@ -125,20 +138,22 @@ struct mpm_handle {
   struct Phase {
     mpm_handle *h;
     Span sp;
-    Phase(mpm_handle *h_, int phase, int launches) : h(h_) {
+    cudaStream_t st;
+    Phase(mpm_handle *h_, int phase, int launches, cudaStream_t on = nullptr) : h(h_), st(on ? on : h_->stream) {
       sp.phase = phase;
       sp.a = sp.b = nullptr;
       if (!h->prof_on) return;
       h->prof.launches[phase] += launches;
       sp.a = h->get_event();
       sp.b = h->get_event();
-      cudaEventRecord(sp.a, h->stream);
+      cudaEventRecord(sp.a, st);
     }
     ~Phase() {
       if (!sp.a) return;
-      cudaEventRecord(sp.b, h->stream);
+      cudaEventRecord(sp.b, st);
       h->spans.push_back(sp);
       if (h->spans.size() >= 8192) {
+        h->join_side();
         cudaStreamSynchronize(h->stream);
         h->flush_spans();
       }
@@ -188,6 +203,12 @@ struct mpm_handle {
       cudaEventDestroy(sp.b);
     }
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+    if (side) {
+      cudaStreamSynchronize(side);
+      cudaStreamDestroy(side);
+    }
+    if (ev_ready) cudaEventDestroy(ev_ready);
+    if (ev_side_done) cudaEventDestroy(ev_side_done);
     if (mig_count_host) cudaFreeHost(mig_count_host);
     if (stats_host) cudaFreeHost(stats_host);
     if (stats_ev) cudaEventDestroy(stats_ev);
@@ -327,6 +348,12 @@ int mpm_handle::init() {
   fused = binned && D == 2 && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE));
   if (fused)
     if ((rc = dalloc(&grid_next, (size_t)nodes))) return rc;
+  overlap = fused && multi && (cfg.flags & MPM_FLAG_OVERLAP);
+  if (overlap) {
+    MPM_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    MPM_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
+    MPM_CUDA(cudaEventCreateWithFlags(&ev_side_done, cudaEventDisableTiming));
+  }
 
   stage_records = cap < (1LL << 22) ? cap : (1LL << 22);  // <= 4M records (224 / 416 MB) per chunk
   if ((rc = dalloc(&stage, (size_t)stage_records * record_words()))) return rc;
@@ -335,6 +362,7 @@ int mpm_handle::init() {
 }
 
 int mpm_handle::upload(const void *aos, const int *ids, long long count, int on_device) {
+  join_side();
   if (count < 0 || (count > 0 && !aos)) {
     err = "upload: bad arguments";
     return MPM_E_INVALID;
@@ -381,6 +409,7 @@ int mpm_handle::upload(const void *aos, const int *ids, long long count, int on_
 
 // keys -> stable sort -> physical reorder into the other SoA buffer; bin_start refreshed
 int mpm_handle::rebin_storage() {
+  join_side();
   if (binned && cfg.rebin_every == 0) {
     // how many particle-steps of the interval that just ended took the fallback path?
     if (stats_pending && cudaEventQuery(stats_ev) == cudaSuccess) {
@@ -415,6 +444,21 @@ int mpm_handle::rebin_storage() {
     MPM_CUDA(cudaStreamSynchronize(stream));
     G.active = active_bins;
     G.n_active = (int)n_active;
+    act_lo_end = 0;
+    act_hi_begin = G.n_active;
+    if (overlap) {
+      // the active list is sorted by bin id (x-major): boundary-lo bins are a prefix, boundary-hi bins a suffix;
+      // the scan scratch still holds "active bins with a smaller id" for every bin
+      const int col = G.nb[1] * G.nb[2];
+      const int lo_bin = cfg.slab_lo > 0 ? (2 < G.nb[0] ? 2 : G.nb[0]) * col : 0;
+      const int hi_bin = cfg.slab_hi < cfg.n_grid ? (G.nb[0] - 2 > 0 ? G.nb[0] - 2 : 0) * col : G.n_bins;
+      unsigned a = 0, b = n_active;
+      MPM_CUDA(cudaMemcpyAsync(&a, active_offs + lo_bin, 4, cudaMemcpyDeviceToHost, stream));
+      MPM_CUDA(cudaMemcpyAsync(&b, active_offs + hi_bin, 4, cudaMemcpyDeviceToHost, stream));
+      MPM_CUDA(cudaStreamSynchronize(stream));
+      act_lo_end = (int)a;
+      act_hi_begin = (int)b > act_lo_end ? (int)b : act_lo_end;
+    }
   }
   MPM_CUDA(cudaGetLastError());
   if (multi) {  // dead (emigrated) slots sorted behind the last bin: drop them from the storage extent
@@ -428,6 +472,7 @@ int mpm_handle::rebin_storage() {
 }
 
 int mpm_handle::read(void *aos_out, long long count, int to_device) {
+  join_side();
   if (count < 0 || count > live || (count > 0 && !aos_out)) {
     err = "read: bad arguments";
     return MPM_E_INVALID;
@@ -452,6 +497,7 @@ int mpm_handle::read(void *aos_out, long long count, int to_device) {
 int mpm_handle::step_p2g(float dt) {
   const bool strict = (cfg.flags & MPM_FLAG_STRICT) != 0;
   if (!(fused && p2g_ready && p2g_dt == dt)) {
+    join_side();
     {
       Phase ph(this, MPM_PHASE_CLEAR, 0);
       MPM_CUDA(cudaMemsetAsync(grid, 0, (size_t)nodes * sizeof(float4), stream));  // :50
@@ -486,6 +532,7 @@ int mpm_handle::step_grid_g2p(float dt) {
     err = "step_grid_g2p: no P2G on the grid (call mpm_step_p2g first)";
     return MPM_E_STATE;
   }
+  join_side();  // the previous substep's interior launch wrote particles and REDs into this grid
   if (grid_tap) {
     MPM_CUDA(cudaMemcpyAsync(grid_tap, grid, (size_t)nodes * sizeof(float4), cudaMemcpyDeviceToDevice, stream));
     tap_valid = true;
@@ -503,6 +550,37 @@ int mpm_handle::step_grid_g2p(float dt) {
       Phase ph(this, MPM_PHASE_CLEAR, 0);
       MPM_CUDA(cudaMemsetAsync(grid_next, 0, (size_t)nodes * sizeof(float4), stream));  // :50 of the next substep
     }
+    if (overlap && act_hi_begin > act_lo_end && D == 2) {
+      // interior bins on the side stream, as soon as the grid update and the clear are done
+      MPM_CUDA(cudaEventRecord(ev_ready, stream));
+      MPM_CUDA(cudaStreamWaitEvent(side, ev_ready, 0));
+      {
+        Phase phs(this, MPM_PHASE_G2P, 1, side);
+        BinGeom Gi = G;
+        Gi.active = G.active + act_lo_end;
+        Gi.n_active = act_hi_begin - act_lo_end;
+        MigPtrs mi = mig;
+        mi.interior = 1;
+        launch_g2p2g<2>(P, Gi, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mi, strict, side);
+      }
+      MPM_CUDA(cudaEventRecord(ev_side_done, side));
+      side_busy = true;
+      // boundary bins (both sides) on the main stream: their emigrants and shared columns are what the
+      // caller exchanges next, while the interior launch is still running
+      Phase ph(this, MPM_PHASE_MIGRATE, 2);  // boundary bins: accounted with the migration work they feed
+      BinGeom Gb = G;
+      Gb.n_active = act_lo_end;
+      if (Gb.n_active > 0)
+        launch_g2p2g<2>(P, Gb, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mig, strict, stream);
+      Gb.active = G.active + act_hi_begin;
+      Gb.n_active = G.n_active - act_hi_begin;
+      if (Gb.n_active > 0)
+        launch_g2p2g<2>(P, Gb, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mig, strict, stream);
+      launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
+      GridPtrs<2> gn = gp<2>();
+      gn.g = grid_next;
+      launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gn, status_dev, stream);
+    } else {
     Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
     if (D == 2) {
       launch_g2p2g<2>(P, G, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mig, strict, stream);
@@ -517,6 +595,7 @@ int mpm_handle::step_grid_g2p(float dt) {
       GridPtrs<3> gn = gp<3>();
       gn.g = grid_next;
       launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gn, status_dev, stream);
+    }
     }
     grid_read = grid;  // the updated grid of this substep stays readable (mpm_read_grid)
     float4 *t = grid;
@@ -571,6 +650,7 @@ int mpm_handle::substep(float dt, int n_steps) {
 }
 
 int mpm_handle::read_grid(int stage_id, float *out) {
+  join_side();
   if (!out || (stage_id != 0 && stage_id != 1)) {
     err = "read_grid: bad arguments";
     return MPM_E_INVALID;
@@ -601,6 +681,7 @@ int mpm_handle::read_grid(int stage_id, float *out) {
 }
 
 int mpm_handle::bin_particles(int *cell, int *key, int *order, int *bin_start_out) {
+  join_side();
   MPM_CUDA(cudaSetDevice(cfg.device));
   if (n == 0) return G.n_bins;
   int rc;
@@ -625,6 +706,7 @@ int mpm_handle::bin_particles(int *cell, int *key, int *order, int *bin_start_ou
 }
 
 int mpm_handle::poll_status() {
+  join_side();
   MPM_CUDA(cudaSetDevice(cfg.device));
   int st = 0;
   MPM_CUDA(cudaMemcpyAsync(&st, status_dev, 4, cudaMemcpyDeviceToHost, stream));
@@ -639,13 +721,14 @@ int mpm_handle::poll_status() {
     return MPM_E_CAPACITY;
   }
   if (st & STATUS_CFL) {
-    err = "a particle crossed more than one bin in one substep";
+    err = "overlapped slab schedule: a particle of an interior bin reached the slab cut (re-sort interval too long)";
     return MPM_E_CFL;
   }
   return MPM_OK;
 }
 
 long long mpm_handle::read_ids(void *aos_out, int *ids_out, long long max_n, int to_device) {
+  join_side();
   if (max_n < n || !aos_out || !ids_out) {
     err = "read_ids: buffers must hold mpm_storage_extent() records";
     return MPM_E_INVALID;
@@ -832,6 +915,7 @@ int mpm_resort(mpm_handle *h) {
 int mpm_synchronize(mpm_handle *h) {
   if (!h) return MPM_E_INVALID;
   cudaSetDevice(h->cfg.device);
+  h->join_side();
   cudaError_t e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) {
     h->err = std::string("synchronize: ") + cudaGetErrorString(e);
@@ -843,6 +927,7 @@ int mpm_poll_status(mpm_handle *h) { return h ? h->poll_status() : MPM_E_INVALID
 int mpm_profile_enable(mpm_handle *h, int on) {
   if (!h) return MPM_E_INVALID;
   cudaSetDevice(h->cfg.device);
+  h->join_side();
   cudaStreamSynchronize(h->stream);
   h->flush_spans();
   memset(&h->prof, 0, sizeof h->prof);
@@ -853,6 +938,7 @@ int mpm_profile_enable(mpm_handle *h, int on) {
 int mpm_profile_read(mpm_handle *h, mpm_profile *out) {
   if (!h || !out) return MPM_E_INVALID;
   cudaSetDevice(h->cfg.device);
+  h->join_side();
   cudaError_t e = cudaStreamSynchronize(h->stream);
   if (e != cudaSuccess) {
     h->err = std::string("profile_read: ") + cudaGetErrorString(e);

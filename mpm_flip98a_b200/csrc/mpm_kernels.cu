@@ -338,7 +338,19 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
         if (MIG) {
           // dead slot: nothing to store; leaving the slab: packed for the neighbour, no P2G here (the
           // receiving handle scatters it when it arrives)
-          if (p.mat != DEAD && !emigrate<D>(P, s, (long long)c0 + i, p, mig, status)) store_state(s, (long long)c0 + i, p);
+          if (p.mat != DEAD) {
+            if (mig.interior) {
+              // overlapped schedule: this launch runs while the slab exchanges its boundary; its bins lie
+              // >= 2 bin columns from the cuts, so nothing here can leave the slab or reach the shared node
+              // columns -- verified, not assumed
+              const int bx = base_coord(p.x[0], P.inv_dx);
+              if ((P.slab_lo > 0 && bx < P.slab_lo + 2) || (P.slab_hi < P.n_grid && bx + 4 > P.slab_hi))
+                atomicOr(status, STATUS_CFL);
+              store_state(s, (long long)c0 + i, p);
+            } else if (!emigrate<D>(P, s, (long long)c0 + i, p, mig, status)) {
+              store_state(s, (long long)c0 + i, p);
+            }
+          }
         } else {
           store_state(s, (long long)c0 + i, p);
         }
@@ -574,11 +586,11 @@ void launch_p2g_cells(const Params &P, const BinGeom &G, float dt, const SoA<D> 
                       GridPtrs<D> g, int *status, unsigned long long *stats, bool strict, cudaStream_t st) {
   if (n <= 0) return;
   if (strict) {
-    if (P.multi) launch_cells_variant<D, false, true, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0}, st);
-    else launch_cells_variant<D, false, false, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0}, st);
+    if (P.multi) launch_cells_variant<D, false, true, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0, 0}, st);
+    else launch_cells_variant<D, false, false, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0, 0}, st);
   } else {
-    if (P.multi) launch_cells_variant<D, true, true, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0}, st);
-    else launch_cells_variant<D, true, false, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0}, st);
+    if (P.multi) launch_cells_variant<D, true, true, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0, 0}, st);
+    else launch_cells_variant<D, true, false, false>(P, G, dt, s, bin_start, g.g, status, stats, nullptr, nullptr, 0.0f, MigPtrs{nullptr, nullptr, nullptr, 0, 0, 0}, st);
   }
 }
 template void launch_p2g_cells<2>(const Params &, const BinGeom &, float, const SoA<2> &, long long, const int *,
