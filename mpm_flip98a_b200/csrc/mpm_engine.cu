@@ -551,8 +551,26 @@ int mpm_handle::step_grid_g2p(float dt) {
       MPM_CUDA(cudaMemsetAsync(grid_next, 0, (size_t)nodes * sizeof(float4), stream));  // :50 of the next substep
     }
     if (overlap && act_hi_begin > act_lo_end && D == 2) {
-      // interior bins on the side stream, as soon as the grid update and the clear are done
-      MPM_CUDA(cudaEventRecord(ev_ready, stream));
+      MPM_CUDA(cudaEventRecord(ev_ready, stream));  // grid updated, next grid cleared
+      {
+        // boundary bins (both sides) FIRST and on the main stream: their emigrants and shared columns are what
+        // the caller exchanges next.  (Enqueued before the interior launch on purpose: the hardware dispatches
+        // CTAs of concurrent kernels in launch order, so the other order would run them after the interior.)
+        Phase ph(this, MPM_PHASE_MIGRATE, 2);  // accounted with the migration work they feed
+        BinGeom Gb = G;
+        Gb.n_active = act_lo_end;
+        if (Gb.n_active > 0)
+          launch_g2p2g<2>(P, Gb, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mig, strict, stream);
+        Gb.active = G.active + act_hi_begin;
+        Gb.n_active = G.n_active - act_hi_begin;
+        if (Gb.n_active > 0)
+          launch_g2p2g<2>(P, Gb, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mig, strict, stream);
+        launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
+        GridPtrs<2> gn = gp<2>();
+        gn.g = grid_next;
+        launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gn, status_dev, stream);
+      }
+      // interior bins on the side stream: run while the caller exchanges the boundary
       MPM_CUDA(cudaStreamWaitEvent(side, ev_ready, 0));
       {
         Phase phs(this, MPM_PHASE_G2P, 1, side);
@@ -565,21 +583,6 @@ int mpm_handle::step_grid_g2p(float dt) {
       }
       MPM_CUDA(cudaEventRecord(ev_side_done, side));
       side_busy = true;
-      // boundary bins (both sides) on the main stream: their emigrants and shared columns are what the
-      // caller exchanges next, while the interior launch is still running
-      Phase ph(this, MPM_PHASE_MIGRATE, 2);  // boundary bins: accounted with the migration work they feed
-      BinGeom Gb = G;
-      Gb.n_active = act_lo_end;
-      if (Gb.n_active > 0)
-        launch_g2p2g<2>(P, Gb, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mig, strict, stream);
-      Gb.active = G.active + act_hi_begin;
-      Gb.n_active = G.n_active - act_hi_begin;
-      if (Gb.n_active > 0)
-        launch_g2p2g<2>(P, Gb, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mig, strict, stream);
-      launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
-      GridPtrs<2> gn = gp<2>();
-      gn.g = grid_next;
-      launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gn, status_dev, stream);
     } else {
     Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
     if (D == 2) {
