@@ -408,7 +408,9 @@ def run_slabs(args, rank, world, local):
     ids = torch.arange(first_id, first_id + n_local, dtype=torch.int32).pin_memory()
     ids_out = torch.empty(int(n_local * 1.1) + 65536, dtype=torch.int32).pin_memory()
 
-    stream = torch.cuda.Stream()
+    # with --overlap the engine's interior launch runs on a lowest-priority side stream; the main stream (boundary
+    # bins, exchange helpers) and NCCL's own stream (TORCH_NCCL_HIGH_PRIORITY, set in __main__) must outrank it
+    stream = torch.cuda.Stream(priority=-1) if args.overlap else torch.cuda.Stream()
     flags = FLAG_NAIVE if args.naive else (32 if args.overlap else 0)
     cap = int(n_local * 1.1) + 65536
     with torch.cuda.stream(stream):
@@ -484,4 +486,6 @@ def run_slabs(args, rank, world, local):
 
 
 if __name__ == "__main__":
+    if "--overlap" in sys.argv:
+        os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
     main()

@@ -350,7 +350,13 @@ int mpm_handle::init() {
     if ((rc = dalloc(&grid_next, (size_t)nodes))) return rc;
   overlap = fused && multi && (cfg.flags & MPM_FLAG_OVERLAP);
   if (overlap) {
-    MPM_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    {
+      // lowest priority: when SM slots free up, boundary kernels (main stream) and the caller's NCCL kernels are
+      // placed before further interior CTAs -- otherwise the many small interior CTAs starve them until the tail
+      int least = 0, greatest = 0;
+      MPM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+      MPM_CUDA(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, least));
+    }
     MPM_CUDA(cudaEventCreateWithFlags(&ev_ready, cudaEventDisableTiming));
     MPM_CUDA(cudaEventCreateWithFlags(&ev_side_done, cudaEventDisableTiming));
   }
