@@ -1,10 +1,14 @@
 // mpm_kernels.cu -- substep kernels, sm_100a.
 //
 // Reference statements each kernel restates (cpp_validation/mls-mpm88-explained.cpp):
-//   k_p2g_*        :53-102   particle -> grid scatter (fused APIC momentum + MLS-MPM stress, :86-89)
-//   k_grid_update  :105-131  normalise by mass, gravity, sticky / separating boundaries
-//   k_g2p_*        :134-179  gather v and C, advect, F update, SVD plasticity clamp, Jp
-// The grid reset (:50) is a cudaMemsetAsync issued by the engine.
+//   k_p2g_naive, k_p2g_cells<FUSED=0>   :53-102   particle -> grid scatter (fused APIC momentum + MLS-MPM stress, :86-89)
+//   k_grid_update                       :105-131  normalise by mass, gravity, sticky / separating boundaries
+//   k_g2p_naive, k_g2p_bins             :134-179  gather v and C, advect, F update, SVD plasticity clamp, Jp
+//   k_p2g_cells<FUSED=1>                :134-179 of substep n, then :53-102 of substep n+1 on the state still in
+//                                       registers -- the default 2D substep kernel
+// The grid reset (:50) is a cudaMemsetAsync issued by the engine.  All arithmetic lives in mpm_math.cuh and is
+// shared with the CPU-side bitwise check (tests/host_check.cpp); this file is about data movement:
+// SoA streams, the per-bin shared-memory cell sort, register accumulation, vector REDs, emigrant packing.
 #include "mpm_kernels.cuh"
 
 namespace mpm {
