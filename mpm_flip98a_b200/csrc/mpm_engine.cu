@@ -433,7 +433,12 @@ int mpm_handle::rebin_storage() {
     }
   }
   steps_since_sort = 0;
-  if (n == 0) return MPM_OK;
+  if (n == 0) {  // nothing resident: no bin holds anything (do not leave the previous upload's ranges behind)
+    n_binned = 0;
+    G.n_active = 0;
+    act_lo_end = act_hi_begin = 0;
+    return MPM_OK;
+  }
   Phase ph(this, MPM_PHASE_BIN, 4 + 3 * ((key_bits + 7) / 8));
   if (D == 2) launch_bin_keys<2>(P, G, s2[cur], n, nullptr, sb.key[0], status_dev, false, stream);
   else launch_bin_keys<3>(P, G, s3[cur], n, nullptr, sb.key[0], status_dev, false, stream);

@@ -221,6 +221,7 @@ def test_roundtrip_and_edge_cases(shipped):
         assert e.count == 0
         e.substep(3)
         assert e.read().shape == (0, 14)
+        assert not e.read_grid(0).any()                         # nothing left behind from the previous upload
         with pytest.raises(mpm.MpmError) as ex:
             e.upload(np.concatenate([p, p]))                    # over capacity
         assert ex.value.code == -3
