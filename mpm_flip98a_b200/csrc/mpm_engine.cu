@@ -812,6 +812,7 @@ int mpm_handle::immigrate(long long n_lo, long long n_hi) {
     return MPM_E_CAPACITY;
   }
   MPM_CUDA(cudaSetDevice(cfg.device));
+  {
   Phase ph(this, MPM_PHASE_MIGRATE, (n_lo ? 1 : 0) + (n_hi ? 1 : 0));
   if (D == 2) {
     launch_immigrate<2>(mig_recv_lo, n_lo, s2[cur], n, stream);
@@ -825,6 +826,7 @@ int mpm_handle::immigrate(long long n_lo, long long n_hi) {
     if (D == 2) launch_p2g_naive<2>(P, p2g_dt, s2[cur], n, n + n_lo + n_hi, gp<2>(), status_dev, stream);
     else launch_p2g_naive<3>(P, p2g_dt, s3[cur], n, n + n_lo + n_hi, gp<3>(), status_dev, stream);
   }
+  }  // the re-sort below is timed under its own phase
   n += n_lo + n_hi;
   live += n_lo + n_hi;
   mig_sent[0] = mig_sent[1] = 0;
