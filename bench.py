@@ -436,6 +436,7 @@ def run_slabs(args, rank, world, local):
         t_wall0 = time.time()
         e0.record(stream)
         parallel.step_dist(r, ex, args.steps)
+        eng.synchronize()  # with --overlap the last interior launch runs on the engine's side stream: join it first
         e1.record(stream)
         torch.cuda.synchronize()
         dist.barrier()
