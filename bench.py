@@ -11,9 +11,14 @@ cpp_validation/mls-mpm88-explained.cpp:49-180) over every particle of the worklo
              the reference's substeps per rendered frame (frame_dt/dt = 10, :11-12,:217)
   roofline   dominant kernel: algorithmic bytes per launch (2D 140 B / 148 B with FLIP,
              3D 260 B per particle-substep, attributed per kernel below) / its mean CUDA-event time
-  cpu_baseline  the oracle's restatement of advance() timed on this box's host, 1 thread (the
-             reference is single-threaded as shipped), on a bounded sample of the same scene
+  cpu_baseline  the oracle's restatement of advance() timed on this box's host on a bounded sample of the same
+             scene: on all host threads (the threaded oracle is bitwise its serial self) and, beside it, on one
+             thread -- the reference is single-threaded as shipped
 `--impl reference` times that CPU path alone and prints the same line with "impl": "reference".
+The timed state is a MOVING scene: c4 starts as a cellular flow (scenes.swirl_velocity, peak speed 3 = 0.024 cells
+per substep, the range of the reference's own scene) and every workload is warmed on the GPU (2000 substeps for
+c4) before anything is timed; the storage re-sorts that fall due run inside the timed steps (their interval is
+capped at K for the timed region so that at least one does), and `resort` / `motion` in the output describe them.
 Synthetic data (mpm_flip98a_b200/scenes.py); nothing here reads /root/reference.
 """
 import argparse
@@ -30,6 +35,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "particle-substeps/sec"
+SWIRL = 3.0  # peak speed of c4's initial cellular flow (scenes.swirl_velocity)
+WARM = {"c2": 3000, "c3": 2000, "c4": 2000, "c5": 1000}  # untimed substeps that put the scene in motion
 FRAME = 10  # substeps per e2e call == the reference's int(frame_dt/dt), mls-mpm88-explained.cpp:217
 
 # algorithmic bytes per particle-substep, per kernel: P2G reads the full record;
@@ -45,6 +52,17 @@ WORKLOADS = {
 }
 
 
+# the GPU tests that cover each benchmarked configuration at full size (pytest -m gpu)
+PARITY_TESTS = {
+    "c2": "tests/test_gpu_parity.py::test_config2_one_warm_substep_full_size",
+    "c3": "tests/test_gpu_fullsize.py::test_config3_full_size (+ _apic)",
+    "c4": "tests/test_gpu_fullsize.py::test_config4_full_size: same scene, same warm-up, 1 substep <= 1e-5 (C: reference "
+          "reorder noise), 10-substep bulk <= 1e-3; fluid/jelly bands and FLIP are north_star extensions whose oracle is "
+          "unpinned by the reference (SURVEY 8a M1-M2)",
+    "c5": "tests/test_gpu_fullsize.py::test_config5_full_size (3D lift: oracle unpinned by the reference, SURVEY 8a M3)",
+}
+
+
 def build_scene(name, n_grid=None):
     from mpm_flip98a_b200 import scenes
     _, dim, n, alpha = WORKLOADS[name]
@@ -54,7 +72,7 @@ def build_scene(name, n_grid=None):
     elif name == "c3":
         p = scenes.dam_break_2d(n, per_side=3, width=0.47)
     elif name == "c4":
-        p = scenes.slab_fill_2d(n, per_side=3)
+        p = scenes.slab_fill_2d(n, per_side=3, swirl=SWIRL)
     else:
         p = scenes.collapse_3d(n, per_side=2)
     dt, vol = scenes.scaled_constants(n, dim)
@@ -98,9 +116,17 @@ class ClockSampler(threading.Thread):
         return out
 
 
-def cpu_sample(name, max_seconds=20.0):
-    """Times the oracle (CPU restatement of advance(), 1 thread) on a bounded sample of the workload:
-    the same scene generator at a reduced grid, warmed by a few substeps.  -> (value, description)."""
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_sample(name, max_seconds=20.0, threads=1):
+    """Times the oracle (CPU restatement of advance()) on a bounded sample of the workload: the same scene
+    generator at a reduced grid, warmed by a few substeps.  threads > 1 = the oracle's threaded loops (bitwise
+    identical results).  -> (value, description, state)."""
     from oracle.cpu import Oracle, build, make_params
     build()
     O = Oracle()
@@ -108,17 +134,18 @@ def cpu_sample(name, max_seconds=20.0):
     n_small = {2: min(n_full, 1024), 3: min(n_full, 96)}[dim]
     p, dim, n, alpha, dt, vol = build_scene(name, n_small)
     P = make_params(dim=dim, n_grid=n, vol_p=vol, alpha=alpha)
-    O.advance(P, dt, p, 1)  # touch everything once
+    O.advance(P, dt, p, 20, threads=host_threads())  # a warm, moving state (not part of the measurement)
     t0 = time.perf_counter()
     steps = 0
     while True:
-        O.advance(P, dt, p, 1)
+        O.advance(P, dt, p, 1, threads=threads)
         steps += 1
         el = time.perf_counter() - t0
         if el > max_seconds or steps >= 50 or (steps >= 3 and el > max_seconds / 2):
             break
     val = len(p) * steps / el
-    desc = "%s scene at n_grid=%d (%d particles), %d substeps, %.1f s" % (name, n, len(p), steps, el)
+    desc = "%s scene at n_grid=%d (%d particles), %d substeps, %.1f s, %d thread%s" % (
+        name, n, len(p), steps, el, threads, "" if threads == 1 else "s")
     return val, desc, (O, P, dt, p)
 
 
@@ -154,16 +181,18 @@ def unmodified_reference_c1(steps=300):
 
 def run_reference(args):
     """Reference arm: the reference's own CPU algorithm for the path (oracle port -- the reference
-    translation unit itself only compiles for its fixed 80^2 scene), single thread as shipped."""
+    translation unit itself only compiles for its fixed 80^2 scene) on ALL host threads this process may use;
+    the single-thread rate (the reference as shipped has no threads) is reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    val, desc, (O, P, dt, p) = cpu_sample(args.workload, max_seconds=5.0)
+    T = host_threads()
+    val1, desc1, (O, P, dt, p) = cpu_sample(args.workload, max_seconds=5.0, threads=1)
     for _ in range(args.warmup):
-        O.advance(P, dt, p, 1)
+        O.advance(P, dt, p, 1, threads=T)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        O.advance(P, dt, p, 1)
+        O.advance(P, dt, p, 1, threads=T)
     el = time.perf_counter() - t0
     value = len(p) * args.steps / el
     descr, dim, n_grid, alpha = WORKLOADS[args.workload]
@@ -174,8 +203,8 @@ def run_reference(args):
             "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": descr, "dim": dim, "n_grid": n_grid, "alpha": alpha, "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "particle-substeps/s", "cores": 1, "kind": "port",
-                             "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "particle-substeps/s", "cores": T, "kind": "port",
+                             "sample": sample, "single_thread_value": val1, "single_thread_sample": desc1},
             "e2e": {"value": value, "unit": "particle-substeps/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "host_cores_total": os.cpu_count(),
@@ -190,10 +219,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--warm-substeps", type=int, default=130,
-                    help="untimed substeps to reach a warm state (the adaptive storage re-sort fires at substeps 16, 32, 64, "
-                         "128, 256, 512: 130 puts a default-length timed region between two of them; the `resort` object "
-                         "of the output reports the re-sort cost and the steady-state rate with it amortised)")
+    ap.add_argument("--warm-substeps", type=int, default=None,
+                    help="untimed substeps that put the scene in motion before anything is timed "
+                         "(default per workload: %s)" % WARM)
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--naive", action="store_true", help="one-thread-per-particle kernels (MPM_FLAG_NAIVE)")
     ap.add_argument("--no-fuse", action="store_true", help="separate P2G and G2P kernels (MPM_FLAG_NO_FUSE)")
@@ -202,6 +230,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rebin-every", type=int, default=0, help="storage re-sort interval (0 = engine default)")
     args = ap.parse_args()
+    if args.warm_substeps is None:
+        args.warm_substeps = WARM[args.workload]
     if args.impl == "reference":
         return run_reference(args)
 
@@ -244,6 +274,23 @@ def main():
             raise SystemExit("engine status %d after warm-up: %s" % (status, eng.lib.mpm_last_error(eng.h)))
 
         # ---- value: K substeps on HBM-resident state, CUDA events on the launching stream -------
+        # long window first (side information): what a substep costs over a few hundred substeps with every
+        # storage re-sort at its own adaptive interval
+        eng.profile_enable(True)
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_long = min(320, max(64, args.warm_substeps // 4))
+        l0.record(stream)
+        eng.substep(n_long)
+        l1.record(stream)
+        torch.cuda.synchronize()
+        long_prof = eng.profile()
+        long_ms = l0.elapsed_time(l1)
+        interval = int(long_prof["rebin_interval"])
+        # timed region: the re-sort interval is capped at K so that at least one re-sort runs INSIDE the K timed
+        # steps whatever their phase (never fewer than the adaptive schedule would run: conservative)
+        timed_interval = max(1, min(interval, args.steps)) if interval > 0 else interval
+        if args.rebin_every == 0 and not args.naive:
+            eng.set_rebin_every(timed_interval)
         for _ in range(args.warmup):
             eng.substep(1)
         eng.synchronize()
@@ -266,15 +313,17 @@ def main():
         clocks = sampler.stop(t_wall0, t_wall1)
         if eng.poll_status() != 0:
             raise SystemExit("engine flagged an error during the timed region")
+        if args.rebin_every == 0 and not args.naive:
+            eng.set_rebin_every(0)
         value = n * args.steps / (ms * 1e-3)
-        # transparency about the periodic storage re-sort: time one re-sort by itself (outside the timed
-        # region) so the line can say what a steady-state substep costs whether or not a re-sort happened
-        # to fall inside the K timed steps (`value` itself is never adjusted)
-        eng.profile_enable(True)
-        eng.resort()
-        resort_ms = eng.profile()["bin"][0]
-        eng.profile_enable(False)
-        prof["resort_ms"] = resort_ms
+        prof["long_window"] = {"substeps": n_long, "ms_per_step": long_ms / n_long,
+                               "value": n * n_long / (long_ms * 1e-3), "adaptive_interval": interval,
+                               "bin_ms_per_step": long_prof["bin"][0] / n_long,
+                               "fallback_fraction": long_prof["fallback_particles"] / float(n * n_long)}
+        prof["timed_interval"] = timed_interval
+        # what the timed state looks like: read it back once (outside any timed region) and sample it
+        eng.lib.mpm_read_particles(eng.h, host_out.data_ptr(), n, 0)
+        prof["motion"] = motion_stats(host_out.numpy()[::257], dim, n_grid, dt)
 
         # ---- e2e: host buffers through the C-ABI, copies inside the timed region ----------------
         eng.lib.mpm_upload_particles(eng.h, host.data_ptr(), n, 0)  # warm the path once
@@ -297,11 +346,45 @@ def main():
     line = make_line(args, world, n, n, words, dim, n_grid, alpha, dt, descr, ms, value, e2e_value, prof, clocks,
                      scaling="weak", extra_config={})
     if not args.no_cpu:
-        val, desc, _ = cpu_sample(args.workload)
-        line["cpu_baseline"] = {"value": val, "unit": "particle-substeps/s", "cores": 1, "kind": "port",
+        T = host_threads()
+        val, desc, _ = cpu_sample(args.workload, max_seconds=12.0, threads=T)
+        val1, desc1, _ = cpu_sample(args.workload, max_seconds=8.0, threads=1)
+        line["cpu_baseline"] = {"value": val, "unit": "particle-substeps/s", "cores": T, "kind": "port",
                                 "sample": desc, "host_cores_total": os.cpu_count(),
+                                "single_thread_value": val1, "single_thread_sample": desc1,
+                                "note": "the reference is single-threaded as shipped; the threaded oracle is bitwise "
+                                        "its serial self",
                                 "unmodified_reference_c1": unmodified_reference_c1()}
     print(json.dumps(line), flush=True)
+
+
+def motion_stats(sample, dim, n_grid, dt):
+    """How dynamic the timed state is (a strided sample of the particles read back after the timed region)."""
+    d, dd = dim, dim * dim
+    v = sample[:, d:2 * d].astype(np.float64)
+    speed = np.sqrt((v ** 2).sum(1))
+    out = {"rms_speed": float(np.sqrt((speed ** 2).mean())), "max_speed": float(speed.max()),
+           "cells_per_substep_rms": float(np.sqrt((speed ** 2).mean()) * dt * n_grid),
+           "cells_per_substep_max": float(speed.max() * dt * n_grid),
+           "rms_velocity_gradient": float(np.sqrt((sample[:, 2 * d + dd:2 * d + 2 * dd].astype(np.float64) ** 2).mean())),
+           "sampled_particles": int(len(sample))}
+    mat = sample[:, -1].view(np.int32)
+    out["material_fractions"] = {str(k): float((mat == k).mean()) for k in np.unique(mat)[:4]}
+    if dim == 2:
+        # snow: which branch of the reference's 2x2 svd the plastic projection takes (taichi.h:8393): the cheap
+        # one needs |S(0,1)| < 1e-6 of the polar factor of (I + dt C) F
+        sn = sample[mat == 2]
+        if len(sn):
+            F = sn[:, 4:8].astype(np.float64).reshape(-1, 2, 2).transpose(0, 2, 1)   # column-major records
+            C = sn[:, 8:12].astype(np.float64).reshape(-1, 2, 2).transpose(0, 2, 1)
+            Fn = (np.eye(2) + dt * C) @ F
+            x, y = Fn[:, 0, 0] + Fn[:, 1, 1], Fn[:, 1, 0] - Fn[:, 0, 1]
+            sc = 1.0 / np.sqrt(x * x + y * y)
+            c, s_ = x * sc, y * sc
+            s01 = c * Fn[:, 0, 1] + s_ * Fn[:, 1, 1]
+            out["snow_svd_general_branch_fraction"] = float((np.abs(s01) >= 1e-6).mean())
+            out["snow_Jp_range"] = [float(sn[:, 12].min()), float(sn[:, 12].max())]
+    return out
 
 
 def make_line(args, world, n_total, n_local, words, dim, n_grid, alpha, dt, descr, ms, value, e2e_value, prof, clocks,
@@ -330,7 +413,7 @@ def make_line(args, world, n_total, n_local, words, dim, n_grid, alpha, dt, desc
     whole = (algo["p2g"] + algo["g2p"]) * value / world / 1e9  # per GPU
     traffic = None
     try:  # measured DRAM bytes per launch of that kernel (ncu --set full, see profiles/), same particle count
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {})
+        t = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json"))).get(args.workload, {})
         if abs(t.get("particles", -1) - n_local) <= 0.01 * n_local:
             traffic = t.get(dom)
     except Exception:
@@ -358,18 +441,22 @@ def make_line(args, world, n_total, n_local, words, dim, n_grid, alpha, dt, desc
                     "call": "mpm_upload_particles + %d substeps + mpm_read_particles, pinned host buffers" % FRAME},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
             "fallback_particles": prof.get("fallback_particles", 0),
-            "resort": resort_info(prof, ms, args.steps, n_total)}
+            "resort": resort_info(prof, ms, args.steps, n_total),
+            "motion": prof.get("motion"),
+            "parity": PARITY_TESTS.get(args.workload)}
 
 
 def resort_info(prof, ms, steps, n_total):
-    """The storage re-sort is periodic (every `interval` substeps, adaptive): say whether one fell inside the
-    timed region, what one costs, and the steady-state rate with its cost amortised over the interval."""
-    out = {"interval_substeps": prof.get("rebin_interval", 0),
-           "ms_inside_timed_region": prof["bin"][0]}
-    if "resort_ms" in prof and out["interval_substeps"] > 0:
-        per_step = (ms - prof["bin"][0]) / steps + prof["resort_ms"] / out["interval_substeps"]
-        out.update(ms_per_resort=prof["resort_ms"], steady_state_ms_per_step=per_step,
-                   steady_state_value=n_total / (per_step * 1e-3))
+    """The storage re-sort is periodic (adaptive interval).  Re-sorts that fall due run INSIDE the timed steps and
+    are part of `value`; this object says how many did, what they cost, and what a long window measures."""
+    out = {"interval_substeps_adaptive": prof.get("long_window", {}).get("adaptive_interval", prof.get("rebin_interval", 0)),
+           "interval_substeps_timed_region": prof.get("timed_interval", prof.get("rebin_interval", 0)),
+           "resorts_inside_timed_region": int(round(prof["bin"][1] / 6.0)) if prof["bin"][1] else 0,
+           "bin_phase_ms_inside_timed_region": prof["bin"][0],
+           "how": "count+rank pass (12 B/particle), scan, then the substep kernel itself writes the new order "
+                  "(RESORT variant); no separate reorder pass on the 2D default path"}
+    if "long_window" in prof:
+        out["long_window"] = prof["long_window"]
     return out
 
 
@@ -394,7 +481,7 @@ def run_slabs(args, rank, world, local):
     # this rank's particles: generate the cell columns that can hold owned base cells, keep the owned
     n_max = scenes.slab_fill_2d_count(n_grid, columns=(lo, hi + 1))
     host = torch.empty((n_max, 14), dtype=torch.float32, pin_memory=True)
-    rec = scenes.slab_fill_2d(n_grid, columns=(lo, hi + 1), out=host.numpy())
+    rec = scenes.slab_fill_2d(n_grid, columns=(lo, hi + 1), out=host.numpy(), swirl=SWIRL)
     b = parallel.base_column(rec[:, 0], n_grid)
     keep = (b >= lo) & (b < hi)
     n_local = int(keep.sum())
@@ -406,13 +493,14 @@ def run_slabs(args, rank, world, local):
     first_id = int(counts[:rank].sum())
     assert n_total < 2 ** 31, "int32 particle ids"
     ids = torch.arange(first_id, first_id + n_local, dtype=torch.int32).pin_memory()
-    ids_out = torch.empty(int(n_local * 1.1) + 65536, dtype=torch.int32).pin_memory()
+    cap = int(n_local * 1.1) + 65536
+    ids_out = torch.empty(cap, dtype=torch.int32).pin_memory()
+    host_out = torch.empty((cap, 14), dtype=torch.float32, pin_memory=True)  # e2e read-back (storage order)
 
     # with --overlap the engine's interior launch runs on a lowest-priority side stream; the main stream (boundary
     # bins, exchange helpers) and NCCL's own stream (TORCH_NCCL_HIGH_PRIORITY, set in __main__) must outrank it
     stream = torch.cuda.Stream(priority=-1) if args.overlap else torch.cuda.Stream()
     flags = FLAG_NAIVE if args.naive else (32 if args.overlap else 0)
-    cap = int(n_local * 1.1) + 65536
     with torch.cuda.stream(stream):
         eng = mpm.Engine(dim=dim, n_grid=n_grid, capacity=cap, dt=dt, vol_p=vol, alpha=alpha, device=local,
                          flags=flags, stream=stream.cuda_stream, rebin_every=args.rebin_every, slab=(lo, hi))
@@ -458,7 +546,7 @@ def run_slabs(args, rank, world, local):
         def e2e_call():
             up()
             parallel.step_dist(r, ex, FRAME)
-            got = eng.lib.mpm_read_particles_ids(eng.h, host.data_ptr(), ids_out.data_ptr(), min(n_max, ids_out.numel()), 0)
+            got = eng.lib.mpm_read_particles_ids(eng.h, host_out.data_ptr(), ids_out.data_ptr(), ids_out.numel(), 0)
             assert got >= 0, eng.lib.mpm_last_error(eng.h)
         e2e_call()
         dist.barrier()

@@ -137,6 +137,8 @@ long long mpm_storage_extent(const mpm_handle *h);
 long long mpm_particle_count(const mpm_handle *h);
 /* Re-sorts the particle storage by bin now (the engine does it on its own every rebin interval). */
 int mpm_resort(mpm_handle *h);
+/* Changes mpm_config.rebin_every of a live handle (0 = back to the adaptive interval). */
+int mpm_set_rebin_every(mpm_handle *h, int every);
 int mpm_synchronize(mpm_handle *h);
 /* Sticky device-side status (MPM_E_DOMAIN, MPM_E_CAPACITY for a migration-buffer overflow) accumulated since
  * the last call; synchronises. */

@@ -35,11 +35,16 @@ struct mpm_handle {
   long long steps_since_sort = 0;
   std::string err;
 
-  // particle storage: two SoA buffers (sorted reorders ping-pong between them)
+  // particle storage: two SoA buffers (re-sorts ping-pong between them).  Each buffer is ONE arena carved into
+  // its arrays, so the idle one can hold a whole AoS image: uploads land there with a single host-to-device copy
+  // and reads leave from there with a single device-to-host copy (no chunked staging).
   std::vector<void *> allocs;
+  char *arena[2] = {nullptr, nullptr};
+  size_t arena_bytes = 0;
   SoA<2> s2[2];
   SoA<3> s3[2];
   int cur = 0;
+  bool plain_ids = true;  // ids are the upload indices 0..n-1 (mpm_upload_particles), not caller-chosen
 
   // grid
   float4 *grid = nullptr, *grid_tap = nullptr;
@@ -83,11 +88,20 @@ struct mpm_handle {
   // binning
   BinGeom G;
   SortBuffers sb;
-  int *bin_start = nullptr;
-  int *active_bins = nullptr;       // compacted ids of the non-empty bins (refreshed by every re-sort)
+  // bin ranges and active-bin lists are double-buffered: during a re-sort substep the kernel walks the OLD order
+  // while it writes the NEW one (bs = index of the set that describes the current storage)
+  int *bin_start_buf[2] = {nullptr, nullptr};
+  int *active_bins_buf[2] = {nullptr, nullptr};  // compacted ids of the non-empty bins
+  int bs = 0;
+  int *bin_start = nullptr;         // == bin_start_buf[bs]
   unsigned *active_offs = nullptr;  // scan scratch, n_bins + 2
   int *cell_dev = nullptr;
   int key_bits = 0;
+  bool resort_due = false;          // the next fused substep re-sorts on the fly (RESORT kernel variant)
+  int *resort_host = nullptr;       // pinned: n_active, live extent, overlap split (lo end, hi begin)
+  cudaEvent_t resort_ev = nullptr;
+  bool resort_pending = false;      // begin_resort() issued, end_resort() not yet
+  bool fused_resort_now = false;    // rebin_storage() called from the fused substep: only the first half
 
   // x-slab exchange (multi == this handle owns a strict sub-range of base-cell columns)
   bool multi = false;
@@ -102,9 +116,6 @@ struct mpm_handle {
   long long halo_nodes() const { return 2LL * P.n1 * (D == 3 ? P.n1 : 1); }
   int mig_words() const { return D == 2 ? MigRec<2>::WORDS : MigRec<3>::WORDS; }
 
-  // AoS staging at the ABI
-  float *stage = nullptr;
-  long long stage_records = 0;
 
   // per-phase CUDA-event timing (mpm_profile_*)
   bool prof_on = false;
@@ -181,6 +192,10 @@ struct mpm_handle {
   int migration_describe(mpm_migration_desc *d);
   int immigrate(long long n_lo, long long n_hi);
   int rebin_storage();
+  int begin_resort();
+  int end_resort();
+  bool fast2d() const { return fused && D == 2 && !(cfg.flags & MPM_FLAG_STRICT); }
+  void carve(int b);
   int substep(float dt, int n_steps);
   int step_p2g(float dt);
   int step_grid_g2p(float dt);
@@ -210,6 +225,8 @@ struct mpm_handle {
     if (ev_ready) cudaEventDestroy(ev_ready);
     if (ev_side_done) cudaEventDestroy(ev_side_done);
     if (mig_count_host) cudaFreeHost(mig_count_host);
+    if (resort_host) cudaFreeHost(resort_host);
+    if (resort_ev) cudaEventDestroy(resort_ev);
     if (stats_host) cudaFreeHost(stats_host);
     if (stats_ev) cudaEventDestroy(stats_ev);
     if (own_stream && stream) cudaStreamDestroy(stream);
@@ -300,17 +317,14 @@ int mpm_handle::init() {
   MPM_CUDA(cudaHostAlloc((void **)&stats_host, 32, cudaHostAllocDefault));
   MPM_CUDA(cudaEventCreateWithFlags(&stats_ev, cudaEventDisableTiming));
 
-  for (int b = 0; b < 2; b++) {
-    if (D == 2) {
-      SoA<2> &s = s2[b];
-      if ((rc = dalloc(&s.x, cap)) || (rc = dalloc(&s.v, cap)) || (rc = dalloc(&s.C, cap)) || (rc = dalloc(&s.F, cap)) ||
-          (rc = dalloc(&s.Jp, cap)) || (rc = dalloc(&s.mat, cap)) || (rc = dalloc(&s.id, cap)))
-        return rc;
-    } else {
-      SoA<3> &s = s3[b];
-      if ((rc = dalloc(&s.xj, cap)) || (rc = dalloc(&s.vm, cap)) || (rc = dalloc(&s.id, cap))) return rc;
-      for (int k = 0; k < 9; k++)
-        if ((rc = dalloc(&s.C[k], cap)) || (rc = dalloc(&s.F[k], cap))) return rc;
+  {
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t c = (size_t)cap;
+    arena_bytes = D == 2 ? 2 * al(c * 8) + 2 * al(c * 16) + 3 * al(c * 4) : 2 * al(c * 16) + 19 * al(c * 4);
+    arena_bytes += 4096;  // an AoS image (56 | 104 B per record) plus its id array always fits: 60 | 108 B per slot
+    for (int b = 0; b < 2; b++) {
+      if ((rc = dalloc(&arena[b], arena_bytes))) return rc;
+      carve(b);
     }
   }
 
@@ -327,7 +341,12 @@ int mpm_handle::init() {
     if ((long long)G.n_bins + 2 > longest) longest = (long long)G.n_bins + 2;
     if ((rc = dalloc(&sb.scan_tmp, scan_tmp_elems(longest)))) return rc;
   }
-  if ((rc = dalloc(&bin_start, (size_t)G.n_bins + 2))) return rc;
+  for (int b = 0; b < 2; b++)
+    if ((rc = dalloc(&bin_start_buf[b], (size_t)G.n_bins + 4)) || (rc = dalloc(&active_bins_buf[b], (size_t)G.n_bins + 1)))
+      return rc;
+  bin_start = bin_start_buf[0];
+  MPM_CUDA(cudaHostAlloc((void **)&resort_host, 32, cudaHostAllocDefault));
+  MPM_CUDA(cudaEventCreateWithFlags(&resort_ev, cudaEventDisableTiming));
   if (multi) {
     mig.cap = (int)(cap / 64 > 4096 ? cap / 64 : 4096);
     mig.enabled = 1;
@@ -342,7 +361,7 @@ int mpm_handle::init() {
     MPM_CUDA(cudaHostAlloc((void **)&mig_count_host, 16, cudaHostAllocDefault));
     mig_count_host[0] = mig_count_host[1] = 0;
   }
-  if ((rc = dalloc(&active_bins, (size_t)G.n_bins + 1)) || (rc = dalloc(&active_offs, (size_t)G.n_bins + 2))) return rc;
+  if ((rc = dalloc(&active_offs, (size_t)G.n_bins + 4))) return rc;
   binned = !(cfg.flags & MPM_FLAG_NAIVE) && (D == 2 ? p2g_cells_supported<2>(G) : p2g_cells_supported<3>(G));
   // 2D only: in 3D the Jacobi-SVD-heavy kernels are compute-bound and fusing them costs occupancy (measured slower)
   fused = binned && D == 2 && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE));
@@ -361,10 +380,36 @@ int mpm_handle::init() {
     MPM_CUDA(cudaEventCreateWithFlags(&ev_side_done, cudaEventDisableTiming));
   }
 
-  stage_records = cap < (1LL << 22) ? cap : (1LL << 22);  // <= 4M records (224 / 416 MB) per chunk
-  if ((rc = dalloc(&stage, (size_t)stage_records * record_words()))) return rc;
   MPM_CUDA(cudaStreamSynchronize(stream));
   return MPM_OK;
+}
+
+void mpm_handle::carve(int b) {
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  char *p = arena[b];
+  const size_t c = (size_t)cap;
+  auto take = [&](size_t bytes) {
+    char *q = p;
+    p += al(bytes);
+    return q;
+  };
+  if (D == 2) {
+    SoA<2> &s = s2[b];
+    s.C = (float4 *)take(c * 16);
+    s.F = (float4 *)take(c * 16);
+    s.x = (float2 *)take(c * 8);
+    s.v = (float2 *)take(c * 8);
+    s.Jp = (float *)take(c * 4);
+    s.mat = (int *)take(c * 4);
+    s.id = (int *)take(c * 4);
+  } else {
+    SoA<3> &s = s3[b];
+    s.xj = (float4 *)take(c * 16);
+    s.vm = (float4 *)take(c * 16);
+    for (int k = 0; k < 9; k++) s.C[k] = (float *)take(c * 4);
+    for (int k = 0; k < 9; k++) s.F[k] = (float *)take(c * 4);
+    s.id = (int *)take(c * 4);
+  }
 }
 
 int mpm_handle::upload(const void *aos, const int *ids, long long count, int on_device) {
@@ -378,32 +423,31 @@ int mpm_handle::upload(const void *aos, const int *ids, long long count, int on_
     return MPM_E_CAPACITY;
   }
   MPM_CUDA(cudaSetDevice(cfg.device));
+  if (resort_pending) end_resort();
   const int W = record_words();
-  for (long long first = 0; first < count; first += stage_records) {
-    long long c = count - first < stage_records ? count - first : stage_records;
-    const float *src = (const float *)aos + first * W;
-    const float *dev_src = src;
+  if (count > 0) {
+    // one copy of the whole AoS image into the idle storage arena, one conversion kernel out of it
+    const float *dev_src = (const float *)aos;
+    const int *dev_ids = ids;
     if (!on_device) {
-      MPM_CUDA(cudaMemcpyAsync(stage, src, (size_t)c * W * 4, cudaMemcpyHostToDevice, stream));
-      dev_src = stage;
-    }
-    const int *dev_ids = nullptr;
-    if (ids) {
-      if (on_device) {
-        dev_ids = ids + first;
-      } else {  // stage the ids behind the records' sort scratch (free during an upload)
-        MPM_CUDA(cudaMemcpyAsync(sb.val[0], ids + first, (size_t)c * 4, cudaMemcpyHostToDevice, stream));
-        dev_ids = sb.val[0];
+      char *img = arena[cur ^ 1];
+      const size_t img_bytes = (size_t)count * W * 4, ids_off = (img_bytes + 255) & ~(size_t)255;
+      MPM_CUDA(cudaMemcpyAsync(img, aos, img_bytes, cudaMemcpyHostToDevice, stream));
+      dev_src = (const float *)img;
+      if (ids) {
+        MPM_CUDA(cudaMemcpyAsync(img + ids_off, ids, (size_t)count * 4, cudaMemcpyHostToDevice, stream));
+        dev_ids = (const int *)(img + ids_off);
       }
     }
-    if (D == 2) launch_aos_to_soa<2>(dev_src, first, c, s2[cur], dev_ids, stream);
-    else launch_aos_to_soa<3>(dev_src, first, c, s3[cur], dev_ids, stream);
-    // the staging buffer is reused by the next chunk; the copy and the kernel are stream-ordered
+    if (D == 2) launch_aos_to_soa<2>(dev_src, 0, count, s2[cur], dev_ids, stream);
+    else launch_aos_to_soa<3>(dev_src, 0, count, s3[cur], dev_ids, stream);
   }
   MPM_CUDA(cudaGetLastError());
   n = count;
   live = count;
+  plain_ids = ids == nullptr;
   p2g_ready = false;
+  resort_due = false;
   grid_read = grid;
   tap_valid = false;
   mig_counts_valid = false;
@@ -413,9 +457,61 @@ int mpm_handle::upload(const void *aos, const int *ids, long long count, int on_
   return MPM_OK;
 }
 
-// keys -> stable sort -> physical reorder into the other SoA buffer; bin_start refreshed
+// First half of a storage re-sort: every slot of the current storage takes (new bin, rank in it) from its current
+// position, the per-bin counts are scanned into the NEW bin starts, the non-empty bins are compacted into the NEW
+// active list, and the few numbers the host needs start their way back.  Everything is enqueued on the stream and
+// nothing waits: the consumer (k_reorder_scatter, or the RESORT substep kernel) is enqueued right behind and
+// end_resort() only synchronises on the small read-back, not on the consumer.
+int mpm_handle::begin_resort() {
+  int *ns = bin_start_buf[bs ^ 1];
+  int *na = active_bins_buf[bs ^ 1];
+  MPM_CUDA(cudaMemsetAsync(ns, 0, ((size_t)G.n_bins + 4) * sizeof(int), stream));
+  if (D == 2) launch_count_rank<2>(P, G, s2[cur], n, (unsigned *)ns, sb.key[0], (unsigned *)sb.val[0], status_dev, stream);
+  else launch_count_rank<3>(P, G, s3[cur], n, (unsigned *)ns, sb.key[0], (unsigned *)sb.val[0], status_dev, stream);
+  // ns[k] = first slot of bin k; ns[n_bins] = live extent (dead slots sort behind every bin); ns[n_bins + 1] = n
+  exclusive_scan_u32((unsigned *)ns, (long long)G.n_bins + 2, sb.scan_tmp, stream);
+  launch_active_bins(ns, G.n_bins, active_offs, sb.scan_tmp, na, stream);
+  MPM_CUDA(cudaMemcpyAsync(&resort_host[0], active_offs + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
+  MPM_CUDA(cudaMemcpyAsync(&resort_host[1], ns + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
+  if (overlap) {
+    // the active list is sorted by bin id (x-major): boundary-lo bins are a prefix, boundary-hi bins a suffix;
+    // the scan scratch holds "active bins with a smaller id" for every bin
+    const int col = G.nb[1] * G.nb[2];
+    const int lo_bin = cfg.slab_lo > 0 ? (2 < G.nb[0] ? 2 : G.nb[0]) * col : 0;
+    const int hi_bin = cfg.slab_hi < cfg.n_grid ? (G.nb[0] - 2 > 0 ? G.nb[0] - 2 : 0) * col : G.n_bins;
+    MPM_CUDA(cudaMemcpyAsync(&resort_host[2], active_offs + lo_bin, 4, cudaMemcpyDeviceToHost, stream));
+    MPM_CUDA(cudaMemcpyAsync(&resort_host[3], active_offs + hi_bin, 4, cudaMemcpyDeviceToHost, stream));
+  }
+  MPM_CUDA(cudaEventRecord(resort_ev, stream));
+  resort_pending = true;
+  return MPM_OK;
+}
+
+// Second half: the consumer has been enqueued; adopt the new order on the host side.
+int mpm_handle::end_resort() {
+  if (!resort_pending) return MPM_OK;
+  MPM_CUDA(cudaEventSynchronize(resort_ev));
+  resort_pending = false;
+  cur ^= 1;
+  bs ^= 1;
+  bin_start = bin_start_buf[bs];
+  G.active = binned ? active_bins_buf[bs] : nullptr;
+  G.n_active = binned ? resort_host[0] : 0;
+  n = resort_host[1];  // dead (emigrated) slots are gone
+  n_binned = n;
+  act_lo_end = 0;
+  act_hi_begin = G.n_active;
+  if (overlap) {
+    act_lo_end = resort_host[2];
+    act_hi_begin = resort_host[3] > act_lo_end ? resort_host[3] : act_lo_end;
+  }
+  return MPM_OK;
+}
+
+// stand-alone re-sort: count + scan, then a scatter of the whole storage into the other buffer
 int mpm_handle::rebin_storage() {
   join_side();
+  if (resort_pending) end_resort();
   if (binned && cfg.rebin_every == 0) {
     // how many particle-steps of the interval that just ended took the fallback path?
     if (stats_pending && cudaEventQuery(stats_ev) == cudaSuccess) {
@@ -433,53 +529,26 @@ int mpm_handle::rebin_storage() {
     }
   }
   steps_since_sort = 0;
+  resort_due = false;
   if (n == 0) {  // nothing resident: no bin holds anything (do not leave the previous upload's ranges behind)
     n_binned = 0;
     G.n_active = 0;
     act_lo_end = act_hi_begin = 0;
     return MPM_OK;
   }
-  Phase ph(this, MPM_PHASE_BIN, 4 + 3 * ((key_bits + 7) / 8));
-  if (D == 2) launch_bin_keys<2>(P, G, s2[cur], n, nullptr, sb.key[0], status_dev, false, stream);
-  else launch_bin_keys<3>(P, G, s3[cur], n, nullptr, sb.key[0], status_dev, false, stream);
-  launch_iota(sb.val[0], n, stream);
-  int r = radix_sort_pairs(sb, n, key_bits, stream);
-  launch_bin_starts(sb.key[r], n, G.n_bins + 1, bin_start, stream);
-  if (D == 2) launch_reorder<2>(s2[cur], s2[cur ^ 1], sb.val[r], n, stream);
-  else launch_reorder<3>(s3[cur], s3[cur ^ 1], sb.val[r], n, stream);
-  cur ^= 1;
-  if (binned) {  // the CTA-per-bin kernels launch over the non-empty bins only
-    launch_active_bins(bin_start, G.n_bins, active_offs, sb.scan_tmp, active_bins, stream);
-    unsigned n_active = 0;
-    MPM_CUDA(cudaMemcpyAsync(&n_active, active_offs + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
-    MPM_CUDA(cudaStreamSynchronize(stream));
-    G.active = active_bins;
-    G.n_active = (int)n_active;
-    act_lo_end = 0;
-    act_hi_begin = G.n_active;
-    if (overlap) {
-      // the active list is sorted by bin id (x-major): boundary-lo bins are a prefix, boundary-hi bins a suffix;
-      // the scan scratch still holds "active bins with a smaller id" for every bin
-      const int col = G.nb[1] * G.nb[2];
-      const int lo_bin = cfg.slab_lo > 0 ? (2 < G.nb[0] ? 2 : G.nb[0]) * col : 0;
-      const int hi_bin = cfg.slab_hi < cfg.n_grid ? (G.nb[0] - 2 > 0 ? G.nb[0] - 2 : 0) * col : G.n_bins;
-      unsigned a = 0, b = n_active;
-      MPM_CUDA(cudaMemcpyAsync(&a, active_offs + lo_bin, 4, cudaMemcpyDeviceToHost, stream));
-      MPM_CUDA(cudaMemcpyAsync(&b, active_offs + hi_bin, 4, cudaMemcpyDeviceToHost, stream));
-      MPM_CUDA(cudaStreamSynchronize(stream));
-      act_lo_end = (int)a;
-      act_hi_begin = (int)b > act_lo_end ? (int)b : act_lo_end;
-    }
+  if (!fused_resort_now) {
+    Phase ph(this, MPM_PHASE_BIN, 7);
+    int rc = begin_resort();
+    if (rc) return rc;
+    const int *ns = bin_start_buf[bs ^ 1];
+    if (D == 2) launch_reorder_scatter<2>(s2[cur], s2[cur ^ 1], 0, n, G.n_bins, ns, sb.key[0], (unsigned *)sb.val[0], stream);
+    else launch_reorder_scatter<3>(s3[cur], s3[cur ^ 1], 0, n, G.n_bins, ns, sb.key[0], (unsigned *)sb.val[0], stream);
+    MPM_CUDA(cudaGetLastError());
+    return end_resort();
   }
-  MPM_CUDA(cudaGetLastError());
-  if (multi) {  // dead (emigrated) slots sorted behind the last bin: drop them from the storage extent
-    int live_extent = 0;
-    MPM_CUDA(cudaMemcpyAsync(&live_extent, bin_start + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
-    MPM_CUDA(cudaStreamSynchronize(stream));
-    n = live_extent;
-  }
-  n_binned = n;
-  return MPM_OK;
+  // on-the-fly variant: the caller (step_grid_g2p) enqueues the RESORT substep kernel as the consumer
+  Phase ph(this, MPM_PHASE_BIN, 6);
+  return begin_resort();
 }
 
 int mpm_handle::read(void *aos_out, long long count, int to_device) {
@@ -489,14 +558,14 @@ int mpm_handle::read(void *aos_out, long long count, int to_device) {
     return MPM_E_INVALID;
   }
   MPM_CUDA(cudaSetDevice(cfg.device));
-  const int W = record_words();
-  for (long long first = 0; first < count; first += stage_records) {
-    long long c = count - first < stage_records ? count - first : stage_records;
-    float *dst = (float *)aos_out + first * W;
-    float *dev_dst = to_device ? dst : stage;
-    if (D == 2) launch_soa_to_aos<2>(s2[cur], n, first, c, dev_dst, nullptr, stream);
-    else launch_soa_to_aos<3>(s3[cur], n, first, c, dev_dst, nullptr, stream);
-    if (!to_device) MPM_CUDA(cudaMemcpyAsync(dst, stage, (size_t)c * W * 4, cudaMemcpyDeviceToHost, stream));
+  if (count > 0) {
+    // one pass: every live particle whose id lies in [0, count) writes its record to image[id]; the image is the
+    // caller's device buffer, or the idle storage arena followed by ONE device-to-host copy
+    const int W = record_words();
+    float *img = to_device ? (float *)aos_out : (float *)arena[cur ^ 1];
+    if (D == 2) launch_soa_to_aos<2>(s2[cur], n, 0, count, img, nullptr, stream);
+    else launch_soa_to_aos<3>(s3[cur], n, 0, count, img, nullptr, stream);
+    if (!to_device) MPM_CUDA(cudaMemcpyAsync(aos_out, img, (size_t)count * W * 4, cudaMemcpyDeviceToHost, stream));
   }
   MPM_CUDA(cudaGetLastError());
   MPM_CUDA(cudaStreamSynchronize(stream));
@@ -561,8 +630,70 @@ int mpm_handle::step_grid_g2p(float dt) {
       Phase ph(this, MPM_PHASE_CLEAR, 0);
       MPM_CUDA(cudaMemsetAsync(grid_next, 0, (size_t)nodes * sizeof(float4), stream));  // :50 of the next substep
     }
+    // 2D default: the packed-math kernel of mpm_substep2d.cu; MPM_FLAG_STRICT (and 3D, if ever fused) keeps
+    // k_p2g_cells<FUSED>.  A due re-sort rides on the fast kernel (RESORT variant): first half here, the kernel
+    // is the consumer, second half after it has been enqueued.
+    const bool fast = fast2d();
+    const bool resort = fast && resort_due && n > 0;
+    if (resort) {
+      fused_resort_now = true;
+      int rc = rebin_storage();
+      fused_resort_now = false;
+      if (rc) return rc;
+    }
+    Substep2dArgs sa;
+    if (fast) {
+      sa.P = P;
+      sa.G = G;
+      sa.dt_g2p = dt;
+      sa.dt_p2g = dt;
+      sa.s = s2[cur];
+      sa.d = s2[cur ^ 1];
+      sa.bin_start = bin_start;
+      sa.new_start = bin_start_buf[bs ^ 1];
+      sa.key = sb.key[0];
+      sa.rank = (const unsigned *)sb.val[0];
+      sa.grid_in = grid;
+      sa.vold_in = (const float2 *)vold;
+      sa.grid_out = grid_next;
+      sa.status = status_dev;
+      sa.stats = stats_dev;
+      sa.mig = mig;
+    }
+    const bool flip = P.alpha != 0.0f;
+    auto run_bins = [&](const BinGeom &Gx, MigPtrs mg, cudaStream_t st) {
+      if (fast) {
+        Substep2dArgs x = sa;
+        x.G = Gx;
+        x.mig = mg;
+        launch_substep2d(x, flip, mg.enabled != 0, resort, st);
+      } else if (D == 2) {
+        launch_g2p2g<2>(P, Gx, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mg, strict, st);
+      } else {
+        launch_g2p2g<3>(P, Gx, dt, dt, s3[cur], n_binned, bin_start, gp<3>(), grid_next, status_dev, stats_dev, mg, strict, st);
+      }
+    };
+    // immigrants since the last re-sort sit behind the binned range: G2P in place, their share of the next P2G,
+    // and -- on a re-sort substep -- their move into the new order
+    auto run_tail = [&]() {
+      if (n <= n_binned) return;
+      if (D == 2) {
+        launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
+        GridPtrs<2> gn = gp<2>();
+        gn.g = grid_next;
+        launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gn, status_dev, stream);
+        if (resort)
+          launch_reorder_scatter<2>(s2[cur], s2[cur ^ 1], n_binned, n, G.n_bins, bin_start_buf[bs ^ 1], sb.key[0],
+                                    (const unsigned *)sb.val[0], stream);
+      } else {
+        launch_g2p_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), mig, status_dev, strict, stream);
+        GridPtrs<3> gn = gp<3>();
+        gn.g = grid_next;
+        launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gn, status_dev, stream);
+      }
+    };
     if (overlap && act_hi_begin > act_lo_end && D == 2) {
-      MPM_CUDA(cudaEventRecord(ev_ready, stream));  // grid updated, next grid cleared
+      MPM_CUDA(cudaEventRecord(ev_ready, stream));  // grid updated, next grid cleared, (re-sort tables ready)
       {
         // boundary bins (both sides) FIRST and on the main stream: their emigrants and shared columns are what
         // the caller exchanges next.  (Enqueued before the interior launch on purpose: the hardware dispatches
@@ -570,16 +701,11 @@ int mpm_handle::step_grid_g2p(float dt) {
         Phase ph(this, MPM_PHASE_MIGRATE, 2);  // accounted with the migration work they feed
         BinGeom Gb = G;
         Gb.n_active = act_lo_end;
-        if (Gb.n_active > 0)
-          launch_g2p2g<2>(P, Gb, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mig, strict, stream);
+        if (Gb.n_active > 0) run_bins(Gb, mig, stream);
         Gb.active = G.active + act_hi_begin;
         Gb.n_active = G.n_active - act_hi_begin;
-        if (Gb.n_active > 0)
-          launch_g2p2g<2>(P, Gb, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mig, strict, stream);
-        launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
-        GridPtrs<2> gn = gp<2>();
-        gn.g = grid_next;
-        launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gn, status_dev, stream);
+        if (Gb.n_active > 0) run_bins(Gb, mig, stream);
+        run_tail();
       }
       // interior bins on the side stream: run while the caller exchanges the boundary
       MPM_CUDA(cudaStreamWaitEvent(side, ev_ready, 0));
@@ -590,26 +716,18 @@ int mpm_handle::step_grid_g2p(float dt) {
         Gi.n_active = act_hi_begin - act_lo_end;
         MigPtrs mi = mig;
         mi.interior = 1;
-        launch_g2p2g<2>(P, Gi, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mi, strict, side);
+        run_bins(Gi, mi, side);
       }
       MPM_CUDA(cudaEventRecord(ev_side_done, side));
       side_busy = true;
     } else {
-    Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
-    if (D == 2) {
-      launch_g2p2g<2>(P, G, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mig, strict, stream);
-      // immigrants since the last re-sort: G2P, then their share of the next P2G
-      launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
-      GridPtrs<2> gn = gp<2>();
-      gn.g = grid_next;
-      launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gn, status_dev, stream);
-    } else {
-      launch_g2p2g<3>(P, G, dt, dt, s3[cur], n_binned, bin_start, gp<3>(), grid_next, status_dev, stats_dev, mig, strict, stream);
-      launch_g2p_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), mig, status_dev, strict, stream);
-      GridPtrs<3> gn = gp<3>();
-      gn.g = grid_next;
-      launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gn, status_dev, stream);
+      Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
+      if (n_binned > 0) run_bins(G, mig, stream);
+      run_tail();
     }
+    if (resort) {
+      int rc = end_resort();
+      if (rc) return rc;
     }
     grid_read = grid;  // the updated grid of this substep stays readable (mpm_read_grid)
     float4 *t = grid;
@@ -653,8 +771,11 @@ int mpm_handle::substep(float dt, int n_steps) {
   for (int s = 0; s < n_steps; s++) {
     int rc;
     const int every = current_interval();
-    if (every > 0 && steps_since_sort >= every)
-      if ((rc = rebin_storage())) return rc;
+    if (every > 0 && steps_since_sort >= every) {
+      // the fast 2D kernel re-sorts on the fly inside this substep; every other path re-sorts stand-alone now
+      if (fast2d() && n > 0) resort_due = true;
+      else if ((rc = rebin_storage())) return rc;
+    }
     if ((rc = step_p2g(dt))) return rc;
     if ((rc = step_grid_g2p(dt))) return rc;
     steps_since_sort++;
@@ -696,6 +817,11 @@ int mpm_handle::read_grid(int stage_id, float *out) {
 
 int mpm_handle::bin_particles(int *cell, int *key, int *order, int *bin_start_out) {
   join_side();
+  if (multi || !plain_ids) {
+    // outputs are indexed by upload order: only defined when the ids ARE the upload indices of one whole set
+    err = "bin_particles: needs a whole-domain handle filled by mpm_upload_particles (ids = upload indices)";
+    return MPM_E_STATE;
+  }
   MPM_CUDA(cudaSetDevice(cfg.device));
   if (n == 0) return G.n_bins;
   int rc;
@@ -748,18 +874,17 @@ long long mpm_handle::read_ids(void *aos_out, int *ids_out, long long max_n, int
     return MPM_E_INVALID;
   }
   MPM_CUDA(cudaSetDevice(cfg.device));
-  const int W = record_words();
-  for (long long first = 0; first < n; first += stage_records) {
-    long long c = n - first < stage_records ? n - first : stage_records;
-    float *dst = (float *)aos_out + first * W;
-    float *dev_dst = to_device ? dst : stage;
-    int *dev_ids = to_device ? ids_out + first : sb.val[0];
-    if (D == 2) launch_soa_to_aos<2>(s2[cur], n, first, c, dev_dst, dev_ids, stream);
-    else launch_soa_to_aos<3>(s3[cur], n, first, c, dev_dst, dev_ids, stream);
+  if (n > 0) {
+    // storage order, one pass; image + ids in the caller's device buffers or in the idle storage arena
+    const int W = record_words();
+    const size_t img_bytes = (size_t)n * W * 4, ids_off = (img_bytes + 255) & ~(size_t)255;
+    float *img = to_device ? (float *)aos_out : (float *)arena[cur ^ 1];
+    int *dev_ids = to_device ? ids_out : (int *)(arena[cur ^ 1] + ids_off);
+    if (D == 2) launch_soa_to_aos<2>(s2[cur], n, 0, n, img, dev_ids, stream);
+    else launch_soa_to_aos<3>(s3[cur], n, 0, n, img, dev_ids, stream);
     if (!to_device) {
-      MPM_CUDA(cudaMemcpyAsync(dst, stage, (size_t)c * W * 4, cudaMemcpyDeviceToHost, stream));
-      MPM_CUDA(cudaMemcpyAsync(ids_out + first, sb.val[0], (size_t)c * 4, cudaMemcpyDeviceToHost, stream));
-      MPM_CUDA(cudaStreamSynchronize(stream));  // staging buffers are reused by the next chunk
+      MPM_CUDA(cudaMemcpyAsync(aos_out, img, img_bytes, cudaMemcpyDeviceToHost, stream));
+      MPM_CUDA(cudaMemcpyAsync(ids_out, dev_ids, (size_t)n * 4, cudaMemcpyDeviceToHost, stream));
     }
   }
   MPM_CUDA(cudaGetLastError());
@@ -807,11 +932,21 @@ int mpm_handle::immigrate(long long n_lo, long long n_hi) {
     err = "immigrate: counts exceed the landing zones";
     return MPM_E_INVALID;
   }
-  if (n + n_lo + n_hi > cap) {
-    err = "immigrate: storage full (capacity must leave room for immigrants between re-sorts)";
-    return MPM_E_CAPACITY;
-  }
   MPM_CUDA(cudaSetDevice(cfg.device));
+  if (n + n_lo + n_hi > cap) {
+    // the storage extent still counts the slots of particles that emigrated since the last re-sort:
+    // compact them away before giving up (the senders have already handed these arrivals over)
+    if (live + n_lo + n_hi > cap) {
+      err = "immigrate: storage full (capacity must leave room for the immigrants)";
+      return MPM_E_CAPACITY;
+    }
+    int rc = rebin_storage();
+    if (rc) return rc;
+    if (n + n_lo + n_hi > cap) {
+      err = "immigrate: storage full after compaction";
+      return MPM_E_CAPACITY;
+    }
+  }
   {
   Phase ph(this, MPM_PHASE_MIGRATE, (n_lo ? 1 : 0) + (n_hi ? 1 : 0));
   if (D == 2) {
@@ -832,7 +967,10 @@ int mpm_handle::immigrate(long long n_lo, long long n_hi) {
   mig_sent[0] = mig_sent[1] = 0;
   steps_since_sort++;
   const int every = current_interval();
-  if (every > 0 && steps_since_sort >= every) return rebin_storage();
+  if (every > 0 && steps_since_sort >= every) {
+    if (fast2d() && n > 0) resort_due = true;  // rides on the next substep kernel
+    else return rebin_storage();
+  }
   MPM_CUDA(cudaGetLastError());
   return MPM_OK;
 }
@@ -927,6 +1065,11 @@ int mpm_resort(mpm_handle *h) {
   if (!h) return MPM_E_INVALID;
   cudaSetDevice(h->cfg.device);
   return h->rebin_storage();
+}
+int mpm_set_rebin_every(mpm_handle *h, int every) {
+  if (!h) return MPM_E_INVALID;
+  h->cfg.rebin_every = every;
+  return MPM_OK;
 }
 int mpm_synchronize(mpm_handle *h) {
   if (!h) return MPM_E_INVALID;

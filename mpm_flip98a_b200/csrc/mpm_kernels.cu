@@ -876,15 +876,18 @@ __global__ void k_soa_to_aos(SoA<D> s, long long n, long long id0, long long cou
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   constexpr int W = 2 * D + 2 * D * D + 2;
-  PState<D> p;
-  load_full(s, i, p);
   long long id = s.id[i];
+  // the filters first: a record that is not wanted costs 8 bytes, not the whole state
   if (ids_out) {  // storage order: records [id0, id0+count) of the storage with their ids (-1 = dead slot)
     if (i < id0 || i >= id0 + count) return;
+  } else if (id < id0 || id >= id0 + count || load_mat(s, i) == DEAD) {
+    return;
+  }
+  PState<D> p;
+  load_full(s, i, p);
+  if (ids_out) {
     ids_out[i - id0] = p.mat == DEAD ? -1 : (int)id;
     id = i;
-  } else if (p.mat == DEAD || id < id0 || id >= id0 + count) {
-    return;
   }
   float *r = aos + (id - id0) * W;
 #pragma unroll

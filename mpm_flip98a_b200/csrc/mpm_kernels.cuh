@@ -50,6 +50,26 @@ template <int D>
 void launch_g2p_bins(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, long long n, const int *bin_start,
                      GridPtrs<D> g, MigPtrs mig, int *status, bool strict, cudaStream_t st);
 
+// ---- the 2D default substep kernel (mpm_substep2d.cu): fused G2P -> P2G, optional on-the-fly re-sort ----
+struct Substep2dArgs {
+  Params P;
+  BinGeom G;
+  float dt_g2p, dt_p2g;
+  SoA<2> s;                   // particle storage (updated in place unless RESORT)
+  SoA<2> d;                   // RESORT: the other storage buffer
+  const int *bin_start;       // bin ranges of `s`
+  const int *new_start;       // RESORT: bin starts of the new order
+  const unsigned *key;        // RESORT: new bin of slot i (k_count_rank, positions before this substep)
+  const unsigned *rank;       // RESORT: rank of slot i inside its new bin
+  const float4 *grid_in;      // updated grid of this substep
+  const float2 *vold_in;      // FLIP: pre-gravity node velocity
+  float4 *grid_out;           // P2G target of the next substep (zeroed)
+  int *status;
+  unsigned long long *stats;
+  MigPtrs mig;
+};
+void launch_substep2d(const Substep2dArgs &a, bool flip, bool mig, bool resort, cudaStream_t st);
+
 // ---- AoS <-> SoA at the C-ABI ------------------------------------------------------------------
 // records [first, first+count) of the caller's AoS -> SoA slots [first, first+count), id = index
 template <int D>
@@ -81,6 +101,13 @@ struct SortBuffers {
 size_t sort_hist_elems(long long n);
 size_t scan_tmp_elems(long long n);
 int radix_sort_pairs(SortBuffers &B, long long n, int bits, cudaStream_t st);
+// storage re-sort by counting (see mpm_sort.cu): counts[n_bins+2] zeroed by the caller and scanned afterwards
+template <int D>
+void launch_count_rank(const Params &P, const BinGeom &G, const SoA<D> &s, long long n, unsigned *counts, unsigned *key,
+                       unsigned *rank, int *status, cudaStream_t st);
+template <int D>
+void launch_reorder_scatter(const SoA<D> &src, const SoA<D> &dst, long long first, long long n, int n_bins,
+                            const int *start, const unsigned *key, const unsigned *rank, cudaStream_t st);
 // bin_start[n_bins+1] from sorted keys
 void launch_bin_starts(const unsigned *sorted_key, long long n, int n_bins, int *bin_start, cudaStream_t st);
 void launch_iota(int *v, long long n, cudaStream_t st);

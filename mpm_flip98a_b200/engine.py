@@ -83,6 +83,7 @@ SYMBOLS = {
     "mpm_storage_extent": (ctypes.c_longlong, [_H]),
     "mpm_particle_count": (ctypes.c_longlong, [_H]),
     "mpm_resort": (ctypes.c_int, [_H]),
+    "mpm_set_rebin_every": (ctypes.c_int, [_H, ctypes.c_int]),
     "mpm_synchronize": (ctypes.c_int, [_H]),
     "mpm_poll_status": (ctypes.c_int, [_H]),
     "mpm_profile_enable": (ctypes.c_int, [_H, ctypes.c_int]),
@@ -244,6 +245,9 @@ class Engine:
 
     def resort(self):
         self._check(self.lib.mpm_resort(self.h))
+
+    def set_rebin_every(self, every):
+        self._check(self.lib.mpm_set_rebin_every(self.h, int(every)))
 
     def synchronize(self):
         self._check(self.lib.mpm_synchronize(self.h))

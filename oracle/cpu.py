@@ -84,6 +84,8 @@ class Oracle:
         L.oracle_advance.restype = ctypes.c_int
         L.oracle_advance.argtypes = [ctypes.c_void_p, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong,
                                      ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.oracle_advance_mt.restype = ctypes.c_int
+        L.oracle_advance_mt.argtypes = L.oracle_advance.argtypes + [ctypes.c_int]
         L.oracle_bin.restype = ctypes.c_int
         L.oracle_bin.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong,
                                  ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
@@ -93,18 +95,20 @@ class Oracle:
         L.oracle_lame.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
         assert L.oracle_params_bytes() == ctypes.sizeof(OracleParams)
 
-    def advance(self, params, dt, particles, n_steps=1, want_grid=False, want_post_p2g=False):
-        """In-place n_steps substeps on an (n, 14|26) float32 AoS array (last word = int32 id)."""
+    def advance(self, params, dt, particles, n_steps=1, want_grid=False, want_post_p2g=False, threads=1):
+        """In-place n_steps substeps on an (n, 14|26) float32 AoS array (last word = int32 id).
+        threads > 1 runs the same loops on several host threads with BITWISE identical results
+        (every grid node still receives its contributions in particle-index order)."""
         assert particles.dtype == np.float32 and particles.flags.c_contiguous
         assert particles.shape[1] == record_words(params.dim)
         n1 = params.n_grid + 1
         shape = (n1,) * params.dim + (params.dim + 1,)
         grid = np.zeros(shape, np.float32) if want_grid else None
         tap = np.zeros(shape, np.float32) if want_post_p2g else None
-        rc = self.lib.oracle_advance(ctypes.byref(params), ctypes.c_float(dt), particles.ctypes.data,
-                                     particles.shape[0], n_steps,
-                                     grid.ctypes.data if grid is not None else None,
-                                     tap.ctypes.data if tap is not None else None)
+        rc = self.lib.oracle_advance_mt(ctypes.byref(params), ctypes.c_float(dt), particles.ctypes.data,
+                                        particles.shape[0], n_steps,
+                                        grid.ctypes.data if grid is not None else None,
+                                        tap.ctypes.data if tap is not None else None, int(threads))
         if rc != 0:
             raise RuntimeError("oracle_advance rc=%d" % rc)
         return grid, tap

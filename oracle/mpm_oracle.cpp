@@ -26,6 +26,7 @@
 #include <cstdint>
 #include <cstring>
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 namespace {
@@ -191,8 +192,51 @@ inline int material_of(const OracleParams &P, int c) {
   return P.n_materials - 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Optional host threading (oracle_advance_mt).  BITWISE identical to the serial loops:
+//   * P2G: thread t owns the node columns [cut[t], cut[t+1]) and walks ALL particles in index order,
+//     adding only the contributions that land in its columns -- so every node still receives its
+//     contributions in particle-index order, exactly like the serial loop (:53-102);
+//   * grid update and G2P touch disjoint nodes / particles and are split by range.
+// n_threads == 1 runs the loops on the calling thread (the reference is single-threaded as shipped).
+// ---------------------------------------------------------------------------------------------
+template <class F>
+void run_threads(int T, F f) {
+  std::vector<std::thread> th;
+  for (int t = 1; t < T; t++) th.emplace_back(f, t);
+  f(0);
+  for (auto &x : th) x.join();
+}
+// base x-column of every particle (:55) and node-column cuts that balance the particle counts
+template <class PT>
+void plan_columns(const PT *particles, long long n, float inv_dx, int N1, int T, std::vector<int> &bx,
+                  std::vector<int> &cut) {
+  bx.resize((size_t)n);
+  run_threads(T, [&](int t) {
+    long long lo = n * t / T, hi = n * (t + 1) / T;
+    for (long long pi = lo; pi < hi; pi++) bx[(size_t)pi] = (int)(particles[pi].x[0] * inv_dx - 0.5f);
+  });
+  std::vector<long long> hist((size_t)N1 + 1, 0);
+  for (long long pi = 0; pi < n; pi++) {
+    int b = bx[(size_t)pi];
+    b = b < 0 ? 0 : (b >= N1 ? N1 - 1 : b);
+    hist[(size_t)b]++;
+  }
+  cut.assign((size_t)T + 1, N1);
+  cut[0] = 0;
+  long long run = 0;
+  int t = 1;
+  for (int c = 0; c < N1 && t < T; c++) {
+    run += hist[(size_t)c];
+    while (t < T && run >= n * t / T) cut[(size_t)t++] = c + 1;
+  }
+  for (int k = 1; k <= T; k++) cut[(size_t)k] = std::max(cut[(size_t)k], cut[(size_t)k - 1]);
+  cut[(size_t)T] = N1;
+}
+
 void advance2(const OracleParams &P, float dt, P2 *particles, long long n, float *grid /*(n+1)^2*3*/,
-              float *grid_post_p2g /*nullable*/, float *vold /*(n+1)^2*2, nullable unless alpha!=0*/) {
+              float *grid_post_p2g /*nullable*/, float *vold /*(n+1)^2*2, nullable unless alpha!=0*/,
+              int n_threads = 1) {
   const int num_grid = P.n_grid;
   const int N1 = num_grid + 1;
   const float dx = 1.0f / num_grid;  // :12
@@ -201,11 +245,21 @@ void advance2(const OracleParams &P, float dt, P2 *particles, long long n, float
   float mu_0[4], lambda_0[4];
   for (int m = 0; m < P.n_materials; m++) lame(P.mat[m].E, P.mat[m].nu, mu_0[m], lambda_0[m]);
   const bool flip = P.alpha != 0.0f;
+  const int T = n_threads > 1 ? n_threads : 1;
+  std::vector<int> bx, cut;
+  if (T > 1) plan_columns(particles, n, inv_dx, N1, T, bx, cut);
+  else cut = {0, N1};
 
-  std::memset(grid, 0, sizeof(float) * 3 * (size_t)N1 * N1);  // :50
+  run_threads(T, [&](int t) {
+  const int col_lo = cut[(size_t)t], col_hi = cut[(size_t)t + 1];  // node columns this thread accumulates
+  std::memset(grid + 3 * (size_t)col_lo * N1, 0, sizeof(float) * 3 * (size_t)(col_hi - col_lo) * N1);  // :50
 
   // P2G :53-102
   for (long long pi = 0; pi < n; pi++) {
+    if (T > 1) {
+      const int b = bx[(size_t)pi];
+      if (b + 2 < col_lo || b >= col_hi) continue;
+    }
     P2 &p = particles[pi];
     const int mid = material_of(P, p.c);
     const OracleMaterial &mat = P.mat[mid];
@@ -249,6 +303,7 @@ void advance2(const OracleParams &P, float dt, P2 *particles, long long n, float
         float ad[2];
         m2_mulvec(affine, dpos, ad);
         float wgt = w[i][0] * w[j][1];
+        if (T > 1 && (base[0] + i < col_lo || base[0] + i >= col_hi)) continue;  // another thread's column
         float *g = grid + 3 * ((size_t)(base[0] + i) * N1 + (base[1] + j));
         g[0] = g[0] + wgt * (mv[0] + ad[0]);
         g[1] = g[1] + wgt * (mv[1] + ad[1]);
@@ -256,10 +311,12 @@ void advance2(const OracleParams &P, float dt, P2 *particles, long long n, float
       }
     }
   }
+  });
   if (grid_post_p2g) std::memcpy(grid_post_p2g, grid, sizeof(float) * 3 * (size_t)N1 * N1);
 
   // grid update :105-131
-  for (int i = 0; i <= num_grid; i++) {
+  run_threads(T, [&](int t) {
+  for (int i = (int)((long long)N1 * t / T); i < (int)((long long)N1 * (t + 1) / T); i++) {
     for (int j = 0; j <= num_grid; j++) {
       float *g = grid + 3 * ((size_t)i * N1 + j);
       if (flip) {
@@ -292,9 +349,11 @@ void advance2(const OracleParams &P, float dt, P2 *particles, long long n, float
       }
     }
   }
+  });
 
   // G2P :134-179
-  for (long long pi = 0; pi < n; pi++) {
+  run_threads(T, [&](int t) {
+  for (long long pi = n * t / T; pi < n * (t + 1) / T; pi++) {
     P2 &p = particles[pi];
     const int mid = material_of(P, p.c);
     const OracleMaterial &mat = P.mat[mid];
@@ -361,6 +420,7 @@ void advance2(const OracleParams &P, float dt, P2 *particles, long long n, float
       p.F = m2_diag(std::sqrt(J));
     }
   }
+  });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -497,7 +557,7 @@ inline void svd3(const M3 &A_in, M3 &U, float sig[3], M3 &V) {
 }
 
 void advance3(const OracleParams &P, float dt, P3 *particles, long long n, float *grid /*(n+1)^3*4*/,
-              float *grid_post_p2g, float *vold /*(n+1)^3*3*/) {
+              float *grid_post_p2g, float *vold /*(n+1)^3*3*/, int n_threads = 1) {
   const int num_grid = P.n_grid;
   const int N1 = num_grid + 1;
   const float dx = 1.0f / num_grid;
@@ -507,9 +567,20 @@ void advance3(const OracleParams &P, float dt, P3 *particles, long long n, float
   for (int m = 0; m < P.n_materials; m++) lame(P.mat[m].E, P.mat[m].nu, mu_0[m], lambda_0[m]);
   const bool flip = P.alpha != 0.0f;
   const size_t NN = (size_t)N1 * N1 * N1;
-  std::memset(grid, 0, sizeof(float) * 4 * NN);
+  const int T = n_threads > 1 ? n_threads : 1;
+  std::vector<int> bx, cut;
+  if (T > 1) plan_columns(particles, n, inv_dx, N1, T, bx, cut);
+  else cut = {0, N1};
+
+  run_threads(T, [&](int t) {
+  const int col_lo = cut[(size_t)t], col_hi = cut[(size_t)t + 1];  // node x-planes this thread accumulates
+  std::memset(grid + 4 * (size_t)col_lo * N1 * N1, 0, sizeof(float) * 4 * (size_t)(col_hi - col_lo) * N1 * N1);
 
   for (long long pi = 0; pi < n; pi++) {
+    if (T > 1) {
+      const int b = bx[(size_t)pi];
+      if (b + 2 < col_lo || b >= col_hi) continue;
+    }
     P3 &p = particles[pi];
     const int mid = material_of(P, p.c);
     const OracleMaterial &mat = P.mat[mid];
@@ -552,6 +623,7 @@ void advance3(const OracleParams &P, float dt, P3 *particles, long long n, float
           float ad[3];
           m3_mulvec(affine, dpos, ad);
           float wgt = w[i][0] * w[j][1] * w[k][2];
+          if (T > 1 && (base[0] + i < col_lo || base[0] + i >= col_hi)) continue;  // another thread's plane
           float *g = grid + 4 * (((size_t)(base[0] + i) * N1 + (base[1] + j)) * N1 + (base[2] + k));
           g[0] = g[0] + wgt * (mass_p * p.v[0] + ad[0]);
           g[1] = g[1] + wgt * (mass_p * p.v[1] + ad[1]);
@@ -559,9 +631,11 @@ void advance3(const OracleParams &P, float dt, P3 *particles, long long n, float
           g[3] = g[3] + wgt * (mass_p + 0.0f);
         }
   }
+  });
   if (grid_post_p2g) std::memcpy(grid_post_p2g, grid, sizeof(float) * 4 * NN);
 
-  for (int i = 0; i <= num_grid; i++)
+  run_threads(T, [&](int t) {
+  for (int i = (int)((long long)N1 * t / T); i < (int)((long long)N1 * (t + 1) / T); i++)
     for (int j = 0; j <= num_grid; j++)
       for (int k = 0; k <= num_grid; k++) {
         size_t node = ((size_t)i * N1 + j) * N1 + k;
@@ -590,8 +664,10 @@ void advance3(const OracleParams &P, float dt, P3 *particles, long long n, float
           if (y < boundary) g[1] = std::max(0.0f, g[1]);
         }
       }
+  });
 
-  for (long long pi = 0; pi < n; pi++) {
+  run_threads(T, [&](int t) {
+  for (long long pi = n * t / T; pi < n * (t + 1) / T; pi++) {
     P3 &p = particles[pi];
     const int mid = material_of(P, p.c);
     const OracleMaterial &mat = P.mat[mid];
@@ -650,6 +726,7 @@ void advance3(const OracleParams &P, float dt, P3 *particles, long long n, float
       p.F = m3_diag(std::cbrt(J));
     }
   }
+  });
 }
 
 // xorshift128, taichi.h:6497-6503 (state is process-wide there; explicit here)
@@ -674,8 +751,9 @@ int oracle_params_bytes() { return (int)sizeof(OracleParams); }
 // n_steps substeps of the 2D/3D restatement on caller-owned AoS records (56 B / 104 B).
 // grid_out: final grid of the last substep ((n+1)^d * (d+1) floats), may be NULL.
 // grid_post_p2g: grid of the LAST substep tapped between P2G and the grid update, may be NULL.
-int oracle_advance(const void *params, float dt, void *particles, long long n, int n_steps, float *grid_out,
-                   float *grid_post_p2g) {
+// n_threads > 1: the same loops on several host threads, bitwise identical to n_threads == 1 (see run_threads).
+int oracle_advance_mt(const void *params, float dt, void *particles, long long n, int n_steps, float *grid_out,
+                      float *grid_post_p2g, int n_threads) {
   const OracleParams &P = *(const OracleParams *)params;
   if (P.dim != 2 && P.dim != 3) return -1;
   if (P.n_materials < 1 || P.n_materials > 4) return -1;
@@ -691,10 +769,14 @@ int oracle_advance(const void *params, float dt, void *particles, long long n, i
   if (P.alpha != 0.0f) vold.resize(nodes * P.dim);
   for (int s = 0; s < n_steps; s++) {
     float *tap = (s == n_steps - 1) ? grid_post_p2g : nullptr;
-    if (P.dim == 2) advance2(P, dt, (P2 *)particles, n, grid, tap, vold.data());
-    else advance3(P, dt, (P3 *)particles, n, grid, tap, vold.data());
+    if (P.dim == 2) advance2(P, dt, (P2 *)particles, n, grid, tap, vold.data(), n_threads);
+    else advance3(P, dt, (P3 *)particles, n, grid, tap, vold.data(), n_threads);
   }
   return 0;
+}
+int oracle_advance(const void *params, float dt, void *particles, long long n, int n_steps, float *grid_out,
+                   float *grid_post_p2g) {
+  return oracle_advance_mt(params, dt, particles, n, n_steps, grid_out, grid_post_p2g, 1);
 }
 
 void oracle_lame(float E, float nu, float *mu0, float *lambda0) { lame(E, nu, *mu0, *lambda0); }

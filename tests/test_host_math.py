@@ -77,3 +77,38 @@ def test_decompositions_bitwise(hc, decomp2, oracle):
         L.hostcheck_svd3(vp(m), vp(U), vp(s), vp(V))
         Uo, so, Vo = oracle.svd3(m)
         assert np.array_equal(bits(np.concatenate([U, s, V])), bits(np.concatenate([Uo, so, Vo])))
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.95])
+def test_packed2d_exact_parts_bitwise(oracle, hc, shipped, alpha):
+    """mpm_math2.cuh (what the default 2D substep kernel calls): stencil2 / affine2 / g2p_finish2 keep the
+    reference association on float2 pairs -> with the exact gather the whole substep is BITWISE the oracle's."""
+    for p0, steps in ((shipped["step0"], 300), (scenes.commented_three_blocks(), 400)):
+        P = make_params(alpha=alpha)
+        a = p0.copy()
+        ga, ta = oracle.advance(P, 1e-4, a, steps, want_grid=True, want_post_p2g=True)
+        H = hc.params(80, 1.0, 1.0, (0.0, -200.0, 0.0), 0.05, 0.6, 20.0, alpha, DEFAULT_MATERIALS)
+        b = p0.copy()
+        gb, tb = hc.advance_packed2(H, 80, 1e-4, b, steps, exact_gather=True)
+        assert np.array_equal(bits(a), bits(b))
+        assert np.array_equal(bits(ga), bits(gb)) and np.array_equal(bits(ta), bits(tb))
+
+
+@pytest.mark.parametrize("alpha", [0.0, 0.95])
+def test_packed2d_fast_gather_one_warm_substep(oracle, hc, shipped, alpha):
+    """The separable FMA gather of the kernel (gather2_row) against the oracle on warm states: the 1e-5 bar
+    of north_star with an order of magnitude to spare (this is arithmetic only -- no atomics on the host)."""
+    from tests.util import fields, rel_l2
+    warm = shipped["step1000"].copy()
+    three = scenes.commented_three_blocks()
+    oracle.advance(make_params(alpha=alpha), 1e-4, three, 1000)
+    for p0 in (warm, three):
+        P = make_params(alpha=alpha)
+        a = p0.copy()
+        oracle.advance(P, 1e-4, a, 1)
+        H = hc.params(80, 1.0, 1.0, (0.0, -200.0, 0.0), 0.05, 0.6, 20.0, alpha, DEFAULT_MATERIALS)
+        b = p0.copy()
+        hc.advance_packed2(H, 80, 1e-4, b, 1, exact_gather=False)
+        fa, fb = fields(a, 2), fields(b, 2)
+        for k in fa:
+            assert rel_l2(fb[k], fa[k]) <= 2e-6, (k, rel_l2(fb[k], fa[k]))
