@@ -92,17 +92,24 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
 
+    def wait_first(self, timeout=5.0):
+        """nvidia-smi needs a moment before its first row: do not open the timed region before it is sampling"""
+        t0 = time.time()
+        while not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
     def stop(self, t0, t1):
         if self.proc:
             self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.03] or [r for t, r in self.rows if t0 - 0.1 <= t <= t1 + 0.1] \
+            or [r for _, r in self.rows]
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(rows)}
         try:
             sm = [float(r[0]) for r in rows]
@@ -297,7 +304,9 @@ def main():
         torch.cuda.synchronize()
         sampler = ClockSampler(local)
         sampler.start()
-        time.sleep(0.3)
+        sampler.wait_first()
+        eng.substep(3)  # the GPU is already under load when the region opens (clock samples are of a busy GPU)
+        eng.synchronize()
         eng.profile_enable(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_wall0 = time.time()
@@ -516,7 +525,7 @@ def run_slabs(args, rank, world, local):
         torch.cuda.synchronize()
         sampler = ClockSampler(local)
         sampler.start()
-        time.sleep(0.3)
+        sampler.wait_first()
         eng.profile_enable(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()

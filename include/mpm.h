@@ -91,8 +91,8 @@ typedef struct mpm_config {
   void *stream;       /* cudaStream_t to launch on; NULL = a stream owned by the handle */
   int bin_edge;       /* cells per bin edge for the block binning; 0 = engine default */
   int rebin_every;    /* re-sort the particle storage by bin every this many substeps; <0 = never;
-                         0 = engine default: 32 on the naive path, adaptive 4..512 on the binned path
-                         (doubled while < 0.1% of particle-steps outrun the 1-cell bin margin) */
+                         0 = engine default: 32 on the naive path, adaptive 2..512 on the binned path
+                         (0.75 cells / the largest per-substep displacement the kernels measure) */
   int reserved[6];
 } mpm_config;
 

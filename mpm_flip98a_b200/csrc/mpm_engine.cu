@@ -71,9 +71,10 @@ struct mpm_handle {
   bool tap_valid = false;
 
   int *status_dev = nullptr;
-  unsigned long long *stats_dev = nullptr;  // [0] = binned-P2G fallback particles (total), [1] = since the last re-sort
-  // adaptive re-sort interval (binned path, cfg.rebin_every == 0): doubled (up to 512) while almost no
-  // particle outruns the 1-cell bin margin between re-sorts, halved (down to 4) when more than 1% do
+  // [0] = binned-P2G fallback particles (total), [1] = since the last re-sort,
+  // [2] = largest displacement of one substep since the last re-sort (float bits, in cells)
+  unsigned long long *stats_dev = nullptr;
+  // adaptive re-sort interval (binned path, cfg.rebin_every == 0), see rebin_storage()
   int rebin_interval = 16;
   unsigned long long *stats_host = nullptr;  // pinned copy of stats_dev taken at each re-sort
   cudaEvent_t stats_ev = nullptr;
@@ -513,17 +514,37 @@ int mpm_handle::rebin_storage() {
   join_side();
   if (resort_pending) end_resort();
   if (binned && cfg.rebin_every == 0) {
-    // how many particle-steps of the interval that just ended took the fallback path?
+    // Adaptive re-sort interval.  The binned kernels tolerate a particle that drifted up to MARGIN = 1 cell out of
+    // its bin; beyond that it takes the per-particle scatter (correct, but as slow as the naive path), and once the
+    // fastest particles have moved a cell the fallback share explodes.  So the interval follows the CFL number the
+    // kernels measure (stats[2] = largest displacement of one substep, in cells, since the previous re-sort):
+    //     interval = 0.75 * MARGIN / displacement,
+    // growing at most 2x per re-sort; a measured fallback share above 0.1 % of particle-steps additionally cuts it
+    // by a quarter (paths whose kernels do not report a displacement only use this second rule, additively
+    // increasing after a clean interval).  The numbers arrive one interval late (asynchronous copy).
     if (stats_pending && cudaEventQuery(stats_ev) == cudaSuccess) {
       const double frac = stats_particle_steps > 0 ? (double)stats_host[1] / (double)stats_particle_steps : 0.0;
-      if (frac < 1e-3 && rebin_interval < 512) rebin_interval *= 2;
-      else if (frac > 1e-2 && rebin_interval > 4) rebin_interval /= 2;
+      float disp = 0.0f;
+      {
+        const unsigned bits = (unsigned)(stats_host[2] & 0xffffffffull);
+        memcpy(&disp, &bits, 4);
+      }
+      int next = rebin_interval;
+      if (disp > 0.0f && disp < 1e3f) {
+        const double target = 0.75 / (double)disp;
+        next = target > 512.0 ? 512 : (int)target;
+        if (next > 2 * rebin_interval) next = 2 * rebin_interval;
+      } else if (frac < 1e-4) {
+        next = rebin_interval + (rebin_interval / 4 > 1 ? rebin_interval / 4 : 1);
+      }
+      if (frac > 1e-3 && next > rebin_interval - rebin_interval / 4) next = rebin_interval - rebin_interval / 4;
+      rebin_interval = next < 2 ? 2 : (next > 512 ? 512 : next);
       stats_pending = false;
     }
     if (!stats_pending && steps_since_sort > 0) {
       MPM_CUDA(cudaMemcpyAsync(stats_host, stats_dev, 32, cudaMemcpyDeviceToHost, stream));
       MPM_CUDA(cudaEventRecord(stats_ev, stream));
-      MPM_CUDA(cudaMemsetAsync(stats_dev + 1, 0, 8, stream));
+      MPM_CUDA(cudaMemsetAsync(stats_dev + 1, 0, 16, stream));
       stats_particle_steps = live * steps_since_sort;
       stats_pending = true;
     }
@@ -744,8 +765,8 @@ int mpm_handle::step_grid_g2p(float dt) {
       if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
       else launch_g2p_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), mig, status_dev, strict, stream);
     } else {
-      if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), mig, status_dev, strict, stream);
-      else launch_g2p_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), mig, status_dev, strict, stream);
+      if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), mig, status_dev, strict, stream, stats_dev);
+      else launch_g2p_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), mig, status_dev, strict, stream, stats_dev);
     }
     p2g_ready = false;
   }

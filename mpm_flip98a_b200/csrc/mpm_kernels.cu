@@ -145,10 +145,12 @@ __device__ __forceinline__ bool emigrate(const Params &P, const SoA<D> &s, long 
 }
 
 // loads particle i, gathers from the grid and returns the NEW state in p (nothing stored yet)
-template <int D, bool FAST, typename Fetch>
+// FLIPC: -1 = alpha is tested at run time; 0 / 1 = compiled for alpha == 0 / != 0 (a run-time flag leaves the
+// whole blend in the instruction stream, predicated off: ~6 issue slots per stencil node)
+template <int D, bool FAST, typename Fetch, int FLIPC = -1>
 __device__ __forceinline__ void g2p_update(const Params &P, float dt, const SoA<D> &s, long long i, const Fetch &fetch,
                                            PState<D> &p, bool loaded = false) {
-  const bool flip = P.alpha != 0.0f;
+  const bool flip = FLIPC < 0 ? (P.alpha != 0.0f) : (FLIPC != 0);
   if (!loaded) load_g2p(s, i, p, flip);
   Stencil<D> st = make_stencil<D>(p.x, P.inv_dx);
   clamp_base<D>(P, st.base);
@@ -176,15 +178,17 @@ __device__ __forceinline__ void g2p_update(const Params &P, float dt, const SoA<
   g2p_finish<D>(P, mat, dt, p.x, p.v, p.C, p.F, p.Jp, v_in, dv);
 }
 
-template <int D, bool MIG, bool FAST, typename Fetch>
-__device__ __forceinline__ void g2p_one(const Params &P, float dt, const SoA<D> &s, long long i, const Fetch &fetch,
+// returns true when the particle was advanced and stored in place (false: dead slot or emigrated)
+template <int D, bool MIG, bool FAST, typename Fetch, int FLIPC = -1>
+__device__ __forceinline__ bool g2p_one(const Params &P, float dt, const SoA<D> &s, long long i, const Fetch &fetch,
                                         const MigPtrs &mig, int *__restrict__ status) {
   PState<D> p;
-  g2p_update<D, FAST>(P, dt, s, i, fetch, p);
+  g2p_update<D, FAST, Fetch, FLIPC>(P, dt, s, i, fetch, p);
   const bool dead = MIG && p.mat == DEAD;  // predicate after the loads were issued, not an early exit
-  if (dead) return;
-  if (MIG && emigrate<D>(P, s, i, p, mig, status)) return;
+  if (dead) return false;
+  if (MIG && emigrate<D>(P, s, i, p, mig, status)) return false;
   store_state(s, i, p);
+  return true;
 }
 
 // nodes straight from global memory through the read-only path
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
       int bad = clamp_base<D>(P, st.base);
       if (bad) atomicOr(status, bad);
       const Material &mat = P.mat[material_index(P, p.mat)];
-      Mat<D> affine = p2g_affine<D>(P, mat, dt, p.F, p.C, p.Jp);
+      Mat<D> affine = p2g_affine<D, FAST>(P, mat, dt, p.F, p.C, p.Jp);  // FAST: Newton polar in 3D (mpm_math.cuh)
       float mv[D];
 #pragma unroll
       for (int c = 0; c < D; c++) mv[c] = P.mass_p * p.v[c];
@@ -634,14 +638,30 @@ template void launch_g2p2g<3>(const Params &, const BinGeom &, float, float, con
 // ------------------------------------------------------------------------------------------------
 // NOTE: no min-blocks hint here on purpose: with one, ptxas front-loads all 3^D node loads (56 regs),
 // which measured 14% slower on B200 than the interleaved schedule it picks without (48 regs).
-template <int D, bool MIG, bool FAST>
+template <int D, bool MIG, bool FAST, bool FLIP>
 __global__ void __launch_bounds__(128) k_g2p_naive(Params P, float dt, SoA<D> s, long long first, long long n,
                                                    const float4 *__restrict__ grid, const void *__restrict__ vold_,
-                                                   MigPtrs mig, int *__restrict__ status) {
+                                                   MigPtrs mig, int *__restrict__ status,
+                                                   unsigned long long *__restrict__ stats) {
   long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  GlobalFetch<D> fetch{grid, vold_};
-  g2p_one<D, MIG, FAST>(P, dt, s, i, fetch, mig, status);
+  float disp = 0.0f;
+  if (i < n) {
+    GlobalFetch<D> fetch{grid, vold_};
+    float x0[D];
+    load_pos(s, i, x0);
+    const bool moved = g2p_one<D, MIG, FAST, GlobalFetch<D>, FLIP ? 1 : 0>(P, dt, s, i, fetch, mig, status);
+    if (moved) {
+      float x1[D];
+      load_pos(s, i, x1);  // just written by this thread
+#pragma unroll
+      for (int k = 0; k < D; k++) disp = fmaxf(disp, fabsf(x1[k] - x0[k]) * P.inv_dx);
+    }
+  }
+  if (stats) {  // largest displacement of this substep in cells: feeds the re-sort interval (see engine)
+    const unsigned bits = __reduce_max_sync(0xffffffffu, __float_as_uint(disp));
+    unsigned *slot = reinterpret_cast<unsigned *>(&stats[2]);
+    if ((threadIdx.x & 31) == 0 && bits > *reinterpret_cast<volatile unsigned *>(slot)) atomicMax(slot, bits);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -769,21 +789,28 @@ template void launch_g2p_bins<3>(const Params &, const BinGeom &, float, const S
 
 template <int D>
 void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long first, long long n, GridPtrs<D> g,
-                      MigPtrs mig, int *status, bool strict, cudaStream_t st) {
+                      MigPtrs mig, int *status, bool strict, cudaStream_t st, unsigned long long *stats) {
   if (n - first <= 0) return;
   unsigned blocks = (unsigned)((n - first + 127) / 128);
-  if (mig.enabled) {
-    if (strict) k_g2p_naive<D, true, false><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status);
-    else k_g2p_naive<D, true, true><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status);
-  } else {
-    if (strict) k_g2p_naive<D, false, false><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status);
-    else k_g2p_naive<D, false, true><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status);
+  const bool flip = P.alpha != 0.0f;
+#define MPM_G2P_NAIVE(MIG_, FAST_)                                                                               \
+  {                                                                                                              \
+    if (flip) k_g2p_naive<D, MIG_, FAST_, true><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status, stats); \
+    else k_g2p_naive<D, MIG_, FAST_, false><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status, stats);     \
   }
+  if (mig.enabled) {
+    if (strict) MPM_G2P_NAIVE(true, false)
+    else MPM_G2P_NAIVE(true, true)
+  } else {
+    if (strict) MPM_G2P_NAIVE(false, false)
+    else MPM_G2P_NAIVE(false, true)
+  }
+#undef MPM_G2P_NAIVE
 }
 template void launch_g2p_naive<2>(const Params &, float, const SoA<2> &, long long, long long, GridPtrs<2>, MigPtrs,
-                                  int *, bool, cudaStream_t);
+                                  int *, bool, cudaStream_t, unsigned long long *);
 template void launch_g2p_naive<3>(const Params &, float, const SoA<3> &, long long, long long, GridPtrs<3>, MigPtrs,
-                                  int *, bool, cudaStream_t);
+                                  int *, bool, cudaStream_t, unsigned long long *);
 
 // ------------------------------------------------------------------------------------------------
 // x-slab exchange helpers: ghost-column sum, immigrant unpack

@@ -27,7 +27,7 @@ void launch_p2g_naive(const Params &P, float dt, const SoA<D> &s, long long firs
                       int *status, cudaStream_t st);
 template <int D>
 void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long first, long long n, GridPtrs<D> g,
-                      MigPtrs mig, int *status, bool strict, cudaStream_t st);
+                      MigPtrs mig, int *status, bool strict, cudaStream_t st, unsigned long long *stats = nullptr);
 // x-slab exchange helpers
 void launch_halo_add(float4 *dst, const float4 *src, long long count, cudaStream_t st);
 template <int D>

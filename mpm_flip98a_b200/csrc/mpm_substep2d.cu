@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
   const float s4 = 4 * P.inv_dx;
   const int x_lo = P.slab_lo, x_hi = min(P.slab_hi, P.n_grid - 1) - 1;  // clamp range of base x (clamp_base)
   unsigned n_fallback = 0;
+  float vmax = 0.0f;  // fastest particle of this thread (max norm): feeds the re-sort interval (CFL), see engine
   for (int c0 = s0; c0 < s1; c0 += CAP) {
     const int m = min(CAP, s1 - c0);
     if (tid < NC) cnt[tid] = 0;
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
         p.C.c0 = mul2(sp2(s4), g.c0);  // the 4*inv_dx of :154, applied once
         p.C.c1 = mul2(sp2(s4), g.c1);
         g2p_finish2(P, mat, A.dt_g2p, p.x, p.v, p.C, p.F, p.Jp, v_in, sub2(g.v, g.vo));
+        vmax = fmaxf(vmax, fmaxf(fabsf(g.v.x), fabsf(g.v.y)));  // advection uses the gathered velocity (:159)
       }
       // ---- where does it go: x-slab emigration, storage slot ----
       bool gone = false;
@@ -304,9 +306,16 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
     }
     if (c0 + CAP < s1) __syncthreads();  // another chunk follows: shared arrays are reused
   }
-  if (A.stats && n_fallback) {
-    atomicAdd(&A.stats[0], (unsigned long long)n_fallback);
-    atomicAdd(&A.stats[1], (unsigned long long)n_fallback);
+  if (A.stats) {
+    if (n_fallback) {
+      atomicAdd(&A.stats[0], (unsigned long long)n_fallback);
+      atomicAdd(&A.stats[1], (unsigned long long)n_fallback);
+    }
+    // largest displacement of this substep in cells (non-negative floats order like their bit patterns); the
+    // atomic is only issued by a warp that raises the maximum
+    const unsigned bits = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax * A.dt_g2p * P.inv_dx));
+    unsigned *slot = reinterpret_cast<unsigned *>(&A.stats[2]);
+    if (lane == 0 && bits > *reinterpret_cast<volatile unsigned *>(slot)) atomicMax(slot, bits);
   }
 }
 

@@ -247,7 +247,8 @@ class Engine:
         self._check(self.lib.mpm_resort(self.h))
 
     def set_rebin_every(self, every):
-        self._check(self.lib.mpm_set_rebin_every(self.h, int(every)))
+        if hasattr(self.lib, "mpm_set_rebin_every"):  # absent from older builds (MPM_LIBRARY A/B runs)
+            self._check(self.lib.mpm_set_rebin_every(self.h, int(every)))
 
     def synchronize(self):
         self._check(self.lib.mpm_synchronize(self.h))

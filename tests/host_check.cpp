@@ -260,6 +260,13 @@ void hostcheck_polar2(const float *m, float *R, float *S) {
   std::memcpy(R, &r, 16);
   std::memcpy(S, &s, 16);
 }
+void hostcheck_rotation3(const float *m, float *R_svd, float *R_newton) {
+  Mat<3> M;
+  std::memcpy(&M, m, 36);
+  Mat<3> a = rotation_of(M), b = rotation_of_fast(M);
+  std::memcpy(R_svd, &a, 36);
+  std::memcpy(R_newton, &b, 36);
+}
 void hostcheck_svd3(const float *m, float *U, float *sig3, float *V) {
   Mat<3> M, u, v;
   std::memcpy(&M, m, 36);

@@ -112,3 +112,42 @@ def test_packed2d_fast_gather_one_warm_substep(oracle, hc, shipped, alpha):
         fa, fb = fields(a, 2), fields(b, 2)
         for k in fa:
             assert rel_l2(fb[k], fa[k]) <= 2e-6, (k, rel_l2(fb[k], fa[k]))
+
+
+def test_polar3_newton_matches_svd_rotation(hc):
+    """The fast 3D rotation factor (Newton polar iteration, binned 3D P2G) against U V^T of the Jacobi SVD that the
+    oracle defines: snow-like (clamped), jelly-like (large stretch and shear) and near-singular / inverted inputs
+    (which must take the SVD fallback and therefore agree exactly)."""
+    rs = np.random.RandomState(11)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+    def rot(m):
+        a, b = np.zeros(9, np.float32), np.zeros(9, np.float32)
+        hc.lib.hostcheck_rotation3(vp(np.ascontiguousarray(m, np.float32)), vp(a), vp(b))
+        return a, b
+
+    def random_rotation():
+        q, r = np.linalg.qr(rs.randn(3, 3))
+        q = q * np.sign(np.diag(r))
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        return q
+
+    worst = 0.0
+    for k in range(3000):
+        U, V = random_rotation(), random_rotation()
+        if k % 3 == 0:
+            sig = rs.uniform(0.975, 1.0075, 3)       # snow after the plastic clamp
+        elif k % 3 == 1:
+            sig = rs.uniform(0.4, 1.8, 3)            # jelly under load
+        else:
+            sig = np.exp(rs.uniform(-2.5, 1.0, 3))   # extreme but proper
+        F = (U * sig) @ V.T
+        a, b = rot(F.T.reshape(-1))                  # column-major storage
+        worst = max(worst, float(np.abs(a - b).max()))
+        R = b.reshape(3, 3).T.astype(np.float64)
+        assert np.abs(R @ R.T - np.eye(3)).max() < 2e-6 and abs(np.linalg.det(R) - 1) < 2e-6
+    assert worst < 1.5e-6, worst
+    for F in (np.diag([1.0, 1.0, -0.5]), np.diag([1.0, 0.0, 1.0]), np.zeros((3, 3)), 1e-4 * np.ones((3, 3))):
+        a, b = rot(F.T.reshape(-1))
+        assert np.array_equal(bits(a), bits(b))      # fallback path == the SVD rotation itself
