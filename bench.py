@@ -232,8 +232,11 @@ def main():
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--naive", action="store_true", help="one-thread-per-particle kernels (MPM_FLAG_NAIVE)")
     ap.add_argument("--no-fuse", action="store_true", help="separate P2G and G2P kernels (MPM_FLAG_NO_FUSE)")
-    ap.add_argument("--overlap", action="store_true",
-                    help="N > 1: interior bins on a side stream while the slab boundary is exchanged (MPM_FLAG_OVERLAP)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="N > 1: plain slab schedule (default: interior bins on a side stream while the slab boundary "
+                         "is exchanged, MPM_FLAG_OVERLAP)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak (per-GPU work of N=1, default) or strong (the N=1 problem cut into N slabs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--rebin-every", type=int, default=0, help="storage re-sort interval (0 = engine default)")
     args = ap.parse_args()
@@ -469,32 +472,68 @@ def resort_info(prof, ms, steps, n_total):
     return out
 
 
+def slab_plan(args, world):
+    """grid size, slab cuts and per-slab scene generator of a multi-GPU run.
+    weak scaling: particles AND grid nodes per GPU stay what one GPU has at N = 1 (2D: n_grid = 8192*sqrt(N);
+    3D: n_grid = 256*cbrt(N)), the domain stays the unit box; strong scaling: the N = 1 problem cut in N."""
+    from mpm_flip98a_b200 import parallel, scenes
+    name = args.workload
+    descr, dim, n0, alpha = WORKLOADS[name]
+    edge = 8 if dim == 2 else 4
+    if args.scaling == "weak":
+        f = world ** (0.5 if dim == 2 else 1.0 / 3.0)
+        align = edge * world if dim == 2 else edge
+        n_grid = int(round(n0 * f / align)) * align
+    else:
+        n_grid = n0
+    x_range = (0.05, 0.95) if name in ("c4", "c5") else (0.05, 0.52)
+    slabs = parallel.partition_filled(n_grid, world, edge, x_range=x_range)  # equal particle counts
+
+    def generate(lo, hi, out=None):
+        if name == "c4":
+            return scenes.slab_fill_2d(n_grid, columns=(lo, hi), out=out, swirl=SWIRL)
+        if name == "c5":
+            return scenes.collapse_3d(n_grid, per_side=2, columns=(lo, hi))
+        rec = scenes.dam_break_2d(n_grid, per_side=3, width=0.47)  # c3: small enough to generate whole
+        return rec[(rec[:, 0] >= np.float32(lo / n_grid)) & (rec[:, 0] < np.float32(hi / n_grid))]
+    return descr, dim, n_grid, alpha, slabs, generate
+
+
 def run_slabs(args, rank, world, local):
-    """N > 1: one x-slab per rank (mpm_flip98a_b200/parallel.py), halo sums + migration over NCCL P2P.
-    Weak scaling: the c4 scene at n_grid = 8192*sqrt(N) (same fill fractions), so particles AND grid
-    nodes per GPU stay what one GPU has at N = 1; the domain stays the unit square."""
+    """N > 1: one x-slab per rank (mpm_flip98a_b200/parallel.py): ONE fixed-size NCCL P2P message per neighbour and
+    substep (ghost-column sums + emigrants), no host synchronisation; by default the interior bins run on a side
+    stream while the boundary is exchanged (MPM_FLAG_OVERLAP)."""
     import torch
     import torch.distributed as dist
     import mpm_flip98a_b200 as mpm
     from mpm_flip98a_b200 import parallel, scenes
-    from mpm_flip98a_b200.engine import FLAG_NAIVE
-    if args.workload != "c4":
-        raise SystemExit("multi-GPU bench is defined on the c4 workload")
-    descr, dim, n0, alpha = WORKLOADS["c4"]
-    align = 8 * world
-    n_grid = int(round(n0 * world ** 0.5 / align)) * align
+    from mpm_flip98a_b200.engine import FLAG_NAIVE, FLAG_OVERLAP
+    if args.workload == "c2":
+        raise SystemExit("multi-GPU bench: workloads c4 (default), c5, c3")
+    descr, dim, n_grid, alpha, slabs, generate = slab_plan(args, world)
+    words = 14 if dim == 2 else 26
     dt, vol = scenes.scaled_constants(n_grid, dim)
-    slabs = parallel.partition_filled(n_grid, world, 8, x_range=(0.05, 0.95))  # equal particle counts
     lo, hi = slabs[rank]
     dev = "cuda:%d" % local
     # this rank's particles: generate the cell columns that can hold owned base cells, keep the owned
-    n_max = scenes.slab_fill_2d_count(n_grid, columns=(lo, hi + 1))
-    host = torch.empty((n_max, 14), dtype=torch.float32, pin_memory=True)
-    rec = scenes.slab_fill_2d(n_grid, columns=(lo, hi + 1), out=host.numpy(), swirl=SWIRL)
-    b = parallel.base_column(rec[:, 0], n_grid)
-    keep = (b >= lo) & (b < hi)
-    n_local = int(keep.sum())
-    host.numpy()[:n_local] = rec[keep]
+    # (generated straight into the pinned upload buffer and compacted in place, chunk by chunk: no second copy)
+    if args.workload == "c4":
+        n_max = scenes.slab_fill_2d_count(n_grid, columns=(lo, hi + 1))
+        host = torch.empty((n_max, words), dtype=torch.float32, pin_memory=True)
+        rec = generate(lo, hi + 1, out=host.numpy())
+    else:
+        rec = generate(lo, hi + 1)
+        host = torch.empty((len(rec), words), dtype=torch.float32, pin_memory=True)
+        host.numpy()[:] = rec
+        rec = host.numpy()[:len(rec)]
+    n_local = 0
+    for c0 in range(0, len(rec), 1 << 22):
+        blk = rec[c0:c0 + (1 << 22)]
+        b = parallel.base_column(blk[:, 0], n_grid)
+        kept = blk[(b >= lo) & (b < hi)]
+        host.numpy()[n_local:n_local + len(kept)] = kept
+        n_local += len(kept)
+    del rec
     counts = torch.zeros(world, dtype=torch.int64, device=dev)
     counts[rank] = n_local
     dist.all_reduce(counts)
@@ -504,12 +543,13 @@ def run_slabs(args, rank, world, local):
     ids = torch.arange(first_id, first_id + n_local, dtype=torch.int32).pin_memory()
     cap = int(n_local * 1.1) + 65536
     ids_out = torch.empty(cap, dtype=torch.int32).pin_memory()
-    host_out = torch.empty((cap, 14), dtype=torch.float32, pin_memory=True)  # e2e read-back (storage order)
+    host_out = torch.empty((cap, words), dtype=torch.float32, pin_memory=True)  # e2e read-back (storage order)
 
-    # with --overlap the engine's interior launch runs on a lowest-priority side stream; the main stream (boundary
-    # bins, exchange helpers) and NCCL's own stream (TORCH_NCCL_HIGH_PRIORITY, set in __main__) must outrank it
-    stream = torch.cuda.Stream(priority=-1) if args.overlap else torch.cuda.Stream()
-    flags = FLAG_NAIVE if args.naive else (32 if args.overlap else 0)
+    overlap = dim == 2 and not args.no_overlap and not args.naive and not args.no_fuse
+    # with the overlapped schedule the engine's interior launch runs on a lowest-priority side stream; the main stream
+    # (boundary bins, exchange helpers) and NCCL's own stream (TORCH_NCCL_HIGH_PRIORITY, set in __main__) outrank it
+    stream = torch.cuda.Stream(priority=-1) if overlap else torch.cuda.Stream()
+    flags = FLAG_NAIVE if args.naive else ((FLAG_OVERLAP if overlap else 0) | (16 if args.no_fuse else 0))
     with torch.cuda.stream(stream):
         eng = mpm.Engine(dim=dim, n_grid=n_grid, capacity=cap, dt=dt, vol_p=vol, alpha=alpha, device=local,
                          flags=flags, stream=stream.cuda_stream, rebin_every=args.rebin_every, slab=(lo, hi))
@@ -517,23 +557,30 @@ def run_slabs(args, rank, world, local):
         up()
         r = parallel.SlabRank(eng, rank, world, dev)
         ex = parallel.DistExchange(r, shared_stream=True)  # engine and NCCL ops are ordered on `stream`
-        parallel.step_dist(r, ex, args.warm_substeps)
+        parallel.step_dist(r, ex, args.warm_substeps, settle=False)
         if eng.poll_status() != 0:
             raise SystemExit("rank %d: engine status after warm-up: %s" % (rank, eng.lib.mpm_last_error(eng.h)))
-        parallel.step_dist(r, ex, args.warmup)
-        dist.barrier()
-        torch.cuda.synchronize()
+        # cap the re-sort interval at K for the timed region (at least one re-sort inside, see the module docstring)
+        interval = int(eng.profile()["rebin_interval"])
+        it = torch.tensor([interval], dtype=torch.int64, device=dev)
+        dist.all_reduce(it, op=dist.ReduceOp.MIN)
+        timed_interval = max(1, min(int(it), args.steps))
+        if args.rebin_every == 0 and not args.naive:
+            eng.set_rebin_every(timed_interval)
+        parallel.step_dist(r, ex, args.warmup, settle=False)
         sampler = ClockSampler(local)
         sampler.start()
         sampler.wait_first()
+        dist.barrier()
+        torch.cuda.synchronize()
         eng.profile_enable(True)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
         torch.cuda.synchronize()
         t_wall0 = time.time()
         e0.record(stream)
-        parallel.step_dist(r, ex, args.steps)
-        eng.synchronize()  # with --overlap the last interior launch runs on the engine's side stream: join it first
+        parallel.step_dist(r, ex, args.steps, settle=False)
+        eng.synchronize()  # the last interior launch runs on the engine's side stream: join it before closing the region
         e1.record(stream)
         torch.cuda.synchronize()
         dist.barrier()
@@ -544,12 +591,20 @@ def run_slabs(args, rank, world, local):
         prof = eng.profile()
         eng.profile_enable(False)
         clocks = sampler.stop(t_wall0, t_wall1)
+        if args.rebin_every == 0 and not args.naive:
+            eng.set_rebin_every(0)
+        eng.slab_settle()
         if eng.poll_status() != 0:
-            raise SystemExit("rank %d: engine flagged an error during the timed region" % rank)
+            raise SystemExit("rank %d: engine flagged an error during the timed region: %s"
+                             % (rank, eng.lib.mpm_last_error(eng.h)))
         live = torch.tensor([eng.count], dtype=torch.int64, device=dev)
         dist.all_reduce(live)
         assert int(live) == n_total, "particles lost in migration: %d != %d" % (int(live), n_total)
         value = n_total * args.steps / (ms * 1e-3)
+        prof["timed_interval"] = timed_interval
+        # device time of this rank's phases vs the wall of the step: what the exchange costs on top of the compute
+        phase_sum = sum(prof[k][0] for k in ("clear", "p2g", "grid", "g2p", "bin", "halo", "migrate")) / args.steps
+        prof["exchange_bubble_ms_per_step"] = ms / args.steps - phase_sum
 
         # ---- e2e: every rank uploads its host buffer, FRAME substeps, reads its particles back -------
         def e2e_call():
@@ -568,22 +623,28 @@ def run_slabs(args, rank, world, local):
         e2e_t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
         e2e_value = n_total * FRAME * args.e2e_calls / float(e2e_t)
+        d = eng.slab()
+        msg_bytes = int(d.bytes)
         eng.close()
     if rank == 0:
-        line = make_line(args, world, n_total, n_local, 14, dim, n_grid, alpha, dt, descr, ms, value, e2e_value, prof,
-                         clocks, scaling="weak",
+        line = make_line(args, world, n_total, n_local, words, dim, n_grid, alpha, dt, descr, ms, value, e2e_value, prof,
+                         clocks, scaling=args.scaling,
                          extra_config={"decomposition": "x-slabs cut for equal particle counts, %d..%d columns per GPU"
                                                         % (min(b - a for a, b in slabs), max(b - a for a, b in slabs)),
-                                       "weak_scaling_rule": "n_grid = 8192*sqrt(N), same fill fractions: particles "
-                                                            "and nodes per GPU as at N=1",
-                                       "exchange": "NCCL P2P: 2 ghost node columns each way + emigrant records"
-                                                   + (", overlapped with the interior bins" if args.overlap else "")})
+                                       "scaling_rule": ("weak: n_grid = %d (N=1: %d), same fill fractions -> particles and "
+                                                        "nodes per GPU as at N=1" % (n_grid, WORKLOADS[args.workload][2]))
+                                       if args.scaling == "weak" else "strong: the N=1 problem cut into N slabs",
+                                       "exchange": "one fixed-size NCCL P2P message per neighbour and substep (%d bytes: "
+                                                   "2 ghost node columns + emigrant count + records), no host "
+                                                   "synchronisation%s" % (msg_bytes, ", overlapped with the interior bins"
+                                                                          if overlap else ""),
+                                       "exchange_bubble_ms_per_step": prof["exchange_bubble_ms_per_step"]})
         print(json.dumps(line), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
 
 if __name__ == "__main__":
-    if "--overlap" in sys.argv:
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "--no-overlap" not in sys.argv:
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
     main()

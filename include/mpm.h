@@ -133,8 +133,8 @@ int mpm_read_grid(mpm_handle *h, int stage, float *out);
  * returns the number of records written. */
 int mpm_upload_particles_ids(mpm_handle *h, const void *aos, const int *ids, long long n, int on_device);
 long long mpm_read_particles_ids(mpm_handle *h, void *aos_out, int *ids_out, long long max_n, int to_device);
-long long mpm_storage_extent(const mpm_handle *h);
-long long mpm_particle_count(const mpm_handle *h);
+long long mpm_storage_extent(mpm_handle *h);  /* x-slab handles: synchronises (the extent lives on the device) */
+long long mpm_particle_count(mpm_handle *h);
 /* Re-sorts the particle storage by bin now (the engine does it on its own every rebin interval). */
 int mpm_resort(mpm_handle *h);
 /* Changes mpm_config.rebin_every of a live handle (0 = back to the adaptive interval). */
@@ -175,37 +175,56 @@ int mpm_profile_read(mpm_handle *h, mpm_profile *out); /* synchronises */
  *   index, bin_start[n_bins+1].  Returns the number of bins or a negative error. */
 int mpm_bin_particles(mpm_handle *h, int *cell, int *key, int *order, int *bin_start);
 
-/* ---- x-slab multi-GPU phases (one handle per GPU; the caller moves the bytes, e.g. with
- * ncclSend/ncclRecv or torch.distributed P2P on the device pointers returned here) ------------ */
-typedef struct mpm_halo_desc {
-  void *send_lo, *send_hi; /* device: partial sums of the 2 node columns shared with the lower / upper slab */
-  void *recv_lo, *recv_hi; /* device: where the neighbour's partial sums must land */
-  long long bytes;         /* bytes per message */
-} mpm_halo_desc;
-int mpm_halo_describe(mpm_handle *h, mpm_halo_desc *d);
-/* One substep of an x-slab, split at its exchange points:
- *   mpm_step_p2g                       clear + P2G of the owned particles
- *   [send_hi -> upper.recv_lo, send_lo -> lower.recv_hi]   2 node columns each way
- *   mpm_step_halo_add(have_lo, have_hi) own partial sums + the neighbour's (commutative: both sides
- *                                      end with bit-identical shared columns)
- *   mpm_step_grid_g2p                  grid update (shared columns redundantly) + G2P; particles whose
- *                                      new base cell left [slab_lo, slab_hi) are packed for migration
- *   mpm_migration_describe             synchronises; counts + buffers of the emigrants
- *   [send_hi[0:n_send_hi] -> upper.recv_lo, send_lo[0:n_send_lo] -> lower.recv_hi]
- *   mpm_step_immigrate(n_lo, n_hi)     appends the immigrants; re-sorts storage when due */
-int mpm_step_p2g(mpm_handle *h, float dt);
-int mpm_step_halo_add(mpm_handle *h, int have_lo, int have_hi);
-int mpm_step_grid_g2p(mpm_handle *h, float dt);
-/* emigrants of the last G2P: device buffers of (record + id) and their counts (host, after sync) */
-typedef struct mpm_migration_desc {
-  void *send_lo, *send_hi;         /* device: packed emigrant records */
-  long long n_send_lo, n_send_hi;  /* counts */
-  void *recv_lo, *recv_hi;         /* device: landing zones */
-  long long recv_capacity;         /* records per landing zone */
-  int record_bytes;                /* 56+8 (2D) or 104+8 (3D): record + int32 id + pad */
-} mpm_migration_desc;
-int mpm_migration_describe(mpm_handle *h, mpm_migration_desc *d);
-int mpm_step_immigrate(mpm_handle *h, long long n_recv_lo, long long n_recv_hi);
+/* ---- x-slab multi-GPU protocol: one handle per GPU owns the base-cell columns [slab_lo, slab_hi) -------------
+ * ONE fixed-size message per neighbour and substep, and no host synchronisation anywhere: the caller only moves
+ * `bytes` from send_hi to the upper neighbour's recv_lo and from send_lo to the lower neighbour's recv_hi
+ * (ncclSend/ncclRecv, torch.distributed P2P, cudaMemcpyPeerAsync ... stream-ordered with the handle's stream).
+ * A message = [partial sums of the 2 node columns shared with that neighbour | 16-byte header: emigrant count |
+ * up to record_capacity emigrant records (the reference's Particle record + persistent id)].  Counts, the storage
+ * extent and the live-particle count stay on the device.
+ *   rc = mpm_slab_begin(h, dt)   after an upload or a change of dt: P2G of the resident particles; returns 1 when
+ *                                messages were staged (exchange them now), 0 when there is nothing to exchange
+ *   mpm_slab_step(h, dt)         consumes the received messages (ghost-column sums -- commutative, so both sides end
+ *                                with bit-identical shared columns; immigrants appended, their P2G share added),
+ *                                then one substep: grid update (shared columns redundantly) and G2P + the NEXT
+ *                                substep's P2G; particles whose new base cell left the slab are packed; stages the
+ *                                next messages.  Exchange after every call.
+ *   mpm_slab_settle(h)           consumes the last messages: every particle resident, grid complete (call it before
+ *                                reading particles back; mpm_slab_step continues from there without an exchange)
+ * MPM_FLAG_OVERLAP: the bins next to the cuts are computed and staged first, the interior follows on a side stream
+ * while the caller's exchange is in flight. */
+typedef struct mpm_slab_desc {
+  void *send_lo, *send_hi; /* device: message for the lower / upper neighbour */
+  void *recv_lo, *recv_hi; /* device: where the lower / upper neighbour's message must land */
+  long long bytes;         /* bytes per message (fixed) */
+  long long halo_bytes;    /* of which ghost-column sums (the header follows them) */
+  int record_bytes;        /* 56+8 (2D) or 104+8 (3D): record + int32 id + pad */
+  int record_capacity;     /* emigrants per message; more in one substep raise MPM_E_CAPACITY in mpm_poll_status */
+  int has_lo, has_hi;      /* neighbours that exist */
+} mpm_slab_desc;
+int mpm_slab_describe(mpm_handle *h, mpm_slab_desc *d);
+int mpm_slab_begin(mpm_handle *h, float dt);
+int mpm_slab_step(mpm_handle *h, float dt);
+int mpm_slab_settle(mpm_handle *h);
+
+/* ---- several GPUs behind one handle (mpm_group.cu): the x-slab protocol above driven from the calling thread, one
+ * slab per entry of `devices` (a device may appear more than once), messages pulled over peer memory
+ * (cudaMemcpyPeerAsync: NVLink where peer access exists), no host synchronisation per substep.  `cfg` describes
+ * the WHOLE domain (slab_lo/slab_hi/device/stream are ignored; capacity = all particles).
+ * replaces: the same statements of main() as the single-GPU calls -- add_object (:191-196), the advance loop
+ * (:214-215), reading `particles` (:220-222). */
+typedef struct mpm_group mpm_group;
+mpm_group *mpm_group_create(const mpm_config *cfg, const int *devices, int n_devices);
+void mpm_group_destroy(mpm_group *g);
+const char *mpm_group_last_error(const mpm_group *g);
+/* cuts the grid into x-slabs of (nearly) equal particle counts and uploads each slab's particles (host records) */
+int mpm_group_upload_particles(mpm_group *g, const void *aos, long long n);
+int mpm_group_substep(mpm_group *g, float dt, int n_steps); /* asynchronous */
+int mpm_group_synchronize(mpm_group *g);
+int mpm_group_read_particles(mpm_group *g, void *aos_out, long long n); /* upload order; synchronises */
+int mpm_group_poll_status(mpm_group *g);
+/* slab k: its device, owned base-cell columns and current particle count (any pointer may be NULL) */
+int mpm_group_slab(const mpm_group *g, int k, int *device, int *slab_lo, int *slab_hi, long long *particles);
 
 #ifdef __cplusplus
 }

@@ -4,5 +4,5 @@ The product is libmpm.so (hand-written sm_100a CUDA, built from csrc/).  This pa
 with ctypes -- the same way ``exec.py`` of the reference would -- and fails
 loudly when the library or a CUDA device is missing: there is no CPU fallback.
 """
-from .engine import Engine, MpmError, Config, Material, load_library, LIB_PATH  # noqa: F401
+from .engine import Engine, Group, MpmError, Config, Material, load_library, LIB_PATH  # noqa: F401
 from . import scenes  # noqa: F401

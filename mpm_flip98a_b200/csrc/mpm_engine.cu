@@ -107,11 +107,17 @@ struct mpm_handle {
   // x-slab exchange (multi == this handle owns a strict sub-range of base-cell columns)
   bool multi = false;
   MigPtrs mig = {nullptr, nullptr, nullptr, 0, 0, 0};
-  float *mig_recv_lo = nullptr, *mig_recv_hi = nullptr;
-  float4 *halo_recv_lo = nullptr, *halo_recv_hi = nullptr, *halo_send_lo = nullptr, *halo_send_hi = nullptr;
-  int *mig_count_host = nullptr;  // pinned, 2 ints
-  long long mig_sent[2] = {0, 0};
-  bool mig_counts_valid = false;
+  // One message per neighbour and substep: [ghost partial sums of the 2 shared node columns | header: emigrant count |
+  // up to K emigrant records].  Fixed size, so the caller's transport needs no counts and the host never waits:
+  // the counts stay on the device (header), and so do the storage extent and the live count (dev_ext).
+  char *msg_send[2] = {nullptr, nullptr}, *msg_recv[2] = {nullptr, nullptr};
+  size_t msg_bytes = 0, msg_hdr = 0;  // msg_hdr = offset of the 16-byte header (== bytes of the ghost columns)
+  int *dev_ext = nullptr;             // device: [0] storage extent, [1] live particles   (multi only)
+  int *hdr(char *m) const { return (int *)(m + msg_hdr); }
+  float *recs(char *m) const { return (float *)(m + msg_hdr + 16); }
+  enum { SLAB_FRESH = 0, SLAB_STAGED = 1, SLAB_SETTLED = 2 };
+  int slab_state = SLAB_FRESH;
+  bool pipelined = false;  // the grid always holds the NEXT substep's P2G (fused kernel, or every x-slab handle)
   long long n_binned = 0;  // storage slots covered by bin_start (slots beyond are immigrants since the last re-sort)
   long long live = 0;      // particles owned (storage extent n also counts dead slots)
   long long halo_nodes() const { return 2LL * P.n1 * (D == 3 ? P.n1 : 1); }
@@ -189,9 +195,13 @@ struct mpm_handle {
   int upload(const void *aos, const int *ids, long long count, int on_device);
   int read(void *aos_out, long long count, int to_device);
   long long read_ids(void *aos_out, int *ids_out, long long max_n, int to_device);
-  int halo_add(int have_lo, int have_hi);
-  int migration_describe(mpm_migration_desc *d);
-  int immigrate(long long n_lo, long long n_hi);
+  int slab_begin(float dt);
+  int slab_step(float dt);
+  int slab_settle();
+  int slab_consume();
+  int slab_stage();
+  int sync_extent();
+  int resident_p2g(float dt);
   int rebin_storage();
   int begin_resort();
   int end_resort();
@@ -225,7 +235,6 @@ struct mpm_handle {
     }
     if (ev_ready) cudaEventDestroy(ev_ready);
     if (ev_side_done) cudaEventDestroy(ev_side_done);
-    if (mig_count_host) cudaFreeHost(mig_count_host);
     if (resort_host) cudaFreeHost(resort_host);
     if (resort_ev) cudaEventDestroy(resort_ev);
     if (stats_host) cudaFreeHost(stats_host);
@@ -349,24 +358,34 @@ int mpm_handle::init() {
   MPM_CUDA(cudaHostAlloc((void **)&resort_host, 32, cudaHostAllocDefault));
   MPM_CUDA(cudaEventCreateWithFlags(&resort_ev, cudaEventDisableTiming));
   if (multi) {
-    mig.cap = (int)(cap / 64 > 4096 ? cap / 64 : 4096);
+    // K = records per message: far above what one substep moves across a cut (a column of cells times the CFL
+    // number), small enough that the fixed-size message stays a few MB
+    long long K = cap / 1024;
+    if (K < 16384) K = 16384;
+    if (K > (1 << 18)) K = 1 << 18;
+    if (K > cap / 4) K = cap / 4 > 64 ? cap / 4 : 64;  // small handles (tests)
+    mig.cap = (int)K;
     mig.enabled = 1;
-    size_t words = (size_t)mig.cap * mig_words();
-    if ((rc = dalloc(&mig.send_lo, words)) || (rc = dalloc(&mig.send_hi, words)) || (rc = dalloc(&mig_recv_lo, words)) ||
-        (rc = dalloc(&mig_recv_hi, words)) || (rc = dalloc(&mig.count, 4)))
-      return rc;
-    if ((rc = dalloc(&halo_recv_lo, (size_t)halo_nodes())) || (rc = dalloc(&halo_recv_hi, (size_t)halo_nodes())) ||
-        (rc = dalloc(&halo_send_lo, (size_t)halo_nodes())) || (rc = dalloc(&halo_send_hi, (size_t)halo_nodes())))
-      return rc;
+    msg_hdr = (size_t)halo_nodes() * sizeof(float4);
+    msg_bytes = msg_hdr + 16 + (size_t)K * mig_words() * 4;
+    for (int k = 0; k < 2; k++)
+      if ((rc = dalloc(&msg_send[k], msg_bytes)) || (rc = dalloc(&msg_recv[k], msg_bytes))) return rc;
+    if ((rc = dalloc(&mig.count, 4)) || (rc = dalloc(&dev_ext, 4))) return rc;
+    mig.send_lo = recs(msg_send[0]);
+    mig.send_hi = recs(msg_send[1]);
+    for (int k = 0; k < 2; k++) {
+      MPM_CUDA(cudaMemsetAsync(msg_send[k], 0, msg_hdr + 16, stream));
+      MPM_CUDA(cudaMemsetAsync(msg_recv[k], 0, msg_hdr + 16, stream));
+    }
     MPM_CUDA(cudaMemsetAsync(mig.count, 0, 16, stream));
-    MPM_CUDA(cudaHostAlloc((void **)&mig_count_host, 16, cudaHostAllocDefault));
-    mig_count_host[0] = mig_count_host[1] = 0;
+    MPM_CUDA(cudaMemsetAsync(dev_ext, 0, 16, stream));
   }
   if ((rc = dalloc(&active_offs, (size_t)G.n_bins + 4))) return rc;
   binned = !(cfg.flags & MPM_FLAG_NAIVE) && (D == 2 ? p2g_cells_supported<2>(G) : p2g_cells_supported<3>(G));
   // 2D only: in 3D the Jacobi-SVD-heavy kernels are compute-bound and fusing them costs occupancy (measured slower)
   fused = binned && D == 2 && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE));
-  if (fused)
+  pipelined = fused || multi;
+  if (pipelined)
     if ((rc = dalloc(&grid_next, (size_t)nodes))) return rc;
   overlap = fused && multi && (cfg.flags & MPM_FLAG_OVERLAP);
   if (overlap) {
@@ -451,7 +470,13 @@ int mpm_handle::upload(const void *aos, const int *ids, long long count, int on_
   resort_due = false;
   grid_read = grid;
   tap_valid = false;
-  mig_counts_valid = false;
+  slab_state = SLAB_FRESH;
+  if (multi) {
+    const int e2[2] = {(int)count, (int)count};
+    MPM_CUDA(cudaMemcpyAsync(dev_ext, e2, 8, cudaMemcpyHostToDevice, stream));
+    MPM_CUDA(cudaStreamSynchronize(stream));  // e2 is on this stack frame
+    MPM_CUDA(cudaMemsetAsync(mig.count, 0, 16, stream));
+  }
   int rc = rebin_storage();
   if (rc) return rc;
   MPM_CUDA(cudaStreamSynchronize(stream));  // the caller may free `aos` on return
@@ -467,8 +492,8 @@ int mpm_handle::begin_resort() {
   int *ns = bin_start_buf[bs ^ 1];
   int *na = active_bins_buf[bs ^ 1];
   MPM_CUDA(cudaMemsetAsync(ns, 0, ((size_t)G.n_bins + 4) * sizeof(int), stream));
-  if (D == 2) launch_count_rank<2>(P, G, s2[cur], n, (unsigned *)ns, sb.key[0], (unsigned *)sb.val[0], status_dev, stream);
-  else launch_count_rank<3>(P, G, s3[cur], n, (unsigned *)ns, sb.key[0], (unsigned *)sb.val[0], status_dev, stream);
+  if (D == 2) launch_count_rank<2>(P, G, s2[cur], n, (unsigned *)ns, sb.key[0], (unsigned *)sb.val[0], status_dev, stream, dev_ext);
+  else launch_count_rank<3>(P, G, s3[cur], n, (unsigned *)ns, sb.key[0], (unsigned *)sb.val[0], status_dev, stream, dev_ext);
   // ns[k] = first slot of bin k; ns[n_bins] = live extent (dead slots sort behind every bin); ns[n_bins + 1] = n
   exclusive_scan_u32((unsigned *)ns, (long long)G.n_bins + 2, sb.scan_tmp, stream);
   launch_active_bins(ns, G.n_bins, active_offs, sb.scan_tmp, na, stream);
@@ -545,7 +570,7 @@ int mpm_handle::rebin_storage() {
       MPM_CUDA(cudaMemcpyAsync(stats_host, stats_dev, 32, cudaMemcpyDeviceToHost, stream));
       MPM_CUDA(cudaEventRecord(stats_ev, stream));
       MPM_CUDA(cudaMemsetAsync(stats_dev + 1, 0, 16, stream));
-      stats_particle_steps = live * steps_since_sort;
+      stats_particle_steps = (multi ? n : live) * steps_since_sort;
       stats_pending = true;
     }
   }
@@ -562,8 +587,10 @@ int mpm_handle::rebin_storage() {
     int rc = begin_resort();
     if (rc) return rc;
     const int *ns = bin_start_buf[bs ^ 1];
-    if (D == 2) launch_reorder_scatter<2>(s2[cur], s2[cur ^ 1], 0, n, G.n_bins, ns, sb.key[0], (unsigned *)sb.val[0], stream);
-    else launch_reorder_scatter<3>(s3[cur], s3[cur ^ 1], 0, n, G.n_bins, ns, sb.key[0], (unsigned *)sb.val[0], stream);
+    if (D == 2) launch_reorder_scatter<2>(s2[cur], s2[cur ^ 1], 0, n, G.n_bins, ns, sb.key[0], (unsigned *)sb.val[0], stream, dev_ext);
+    else launch_reorder_scatter<3>(s3[cur], s3[cur ^ 1], 0, n, G.n_bins, ns, sb.key[0], (unsigned *)sb.val[0], stream, dev_ext);
+    if (multi)  // the new extent (dead slots dropped) = first slot of the "dead" bin
+      launch_slab_counters(dev_ext, nullptr, nullptr, nullptr, nullptr, 0, cap, ns + G.n_bins, stream);
     MPM_CUDA(cudaGetLastError());
     return end_resort();
   }
@@ -574,6 +601,7 @@ int mpm_handle::rebin_storage() {
 
 int mpm_handle::read(void *aos_out, long long count, int to_device) {
   join_side();
+  if (multi) sync_extent();
   if (count < 0 || count > live || (count > 0 && !aos_out)) {
     err = "read: bad arguments";
     return MPM_E_INVALID;
@@ -593,37 +621,39 @@ int mpm_handle::read(void *aos_out, long long count, int to_device) {
   return MPM_OK;
 }
 
-// Phase 1 of a substep: grid reset + P2G (:50-102).  On the fused schedule the grid usually already holds
-// this P2G (the previous substep's fused kernel produced it) and nothing is launched.
-int mpm_handle::step_p2g(float dt) {
+// grid reset + P2G of every resident particle into `grid` (:50-102)
+int mpm_handle::resident_p2g(float dt) {
   const bool strict = (cfg.flags & MPM_FLAG_STRICT) != 0;
-  if (!(fused && p2g_ready && p2g_dt == dt)) {
-    join_side();
-    {
-      Phase ph(this, MPM_PHASE_CLEAR, 0);
-      MPM_CUDA(cudaMemsetAsync(grid, 0, (size_t)nodes * sizeof(float4), stream));  // :50
-    }
-    Phase ph(this, MPM_PHASE_P2G, n > 0 ? 1 : 0);
-    if (binned) {
-      if (D == 2) launch_p2g_cells<2>(P, G, dt, s2[cur], n_binned, bin_start, gp<2>(), status_dev, stats_dev, strict, stream);
-      else launch_p2g_cells<3>(P, G, dt, s3[cur], n_binned, bin_start, gp<3>(), status_dev, stats_dev, strict, stream);
-      // immigrants since the last re-sort sit behind the binned range: per-particle scatter
-      if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), status_dev, stream);
-      else launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), status_dev, stream);
-    } else {
-      if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), status_dev, stream);
-      else launch_p2g_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), status_dev, stream);
-    }
+  join_side();
+  {
+    Phase ph(this, MPM_PHASE_CLEAR, 0);
+    MPM_CUDA(cudaMemsetAsync(grid, 0, (size_t)nodes * sizeof(float4), stream));  // :50
+  }
+  Phase ph(this, MPM_PHASE_P2G, n > 0 ? 1 : 0);
+  if (binned) {
+    if (D == 2) launch_p2g_cells<2>(P, G, dt, s2[cur], n_binned, bin_start, gp<2>(), status_dev, stats_dev, strict, stream);
+    else launch_p2g_cells<3>(P, G, dt, s3[cur], n_binned, bin_start, gp<3>(), status_dev, stats_dev, strict, stream);
+    // immigrants since the last re-sort sit behind the binned range: per-particle scatter
+    if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), status_dev, stream, dev_ext);
+    else launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), status_dev, stream, dev_ext);
+  } else {
+    if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), status_dev, stream, dev_ext);
+    else launch_p2g_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), status_dev, stream, dev_ext);
   }
   p2g_ready = true;  // `grid` holds P2G(dt) of the current particle state
   p2g_dt = dt;
   grid_read = grid;
-  if (multi) {  // the two node columns shared with each neighbour, staged at fixed addresses
-    const size_t hb = (size_t)halo_nodes() * sizeof(float4);
-    MPM_CUDA(cudaMemcpyAsync(halo_send_lo, grid, hb, cudaMemcpyDeviceToDevice, stream));
-    MPM_CUDA(cudaMemcpyAsync(halo_send_hi, grid + (nodes - halo_nodes()), hb, cudaMemcpyDeviceToDevice, stream));
-  }
   return MPM_OK;
+}
+
+// Phase 1 of a substep: grid reset + P2G (:50-102).  On the pipelined schedule the grid usually already holds
+// this P2G (the previous substep produced it) and nothing is launched.
+int mpm_handle::step_p2g(float dt) {
+  if (pipelined && p2g_ready && p2g_dt == dt) {
+    grid_read = grid;
+    return MPM_OK;
+  }
+  return resident_p2g(dt);
 }
 
 // Phases 2+3: grid update (:105-131) and G2P (:134-179).  Fused schedule: G2P runs in one kernel with the
@@ -646,6 +676,10 @@ int mpm_handle::step_grid_g2p(float dt) {
   // exact association everywhere under MPM_FLAG_STRICT and on the naive path (the bit-faithful modes)
   const bool strict = (cfg.flags & (MPM_FLAG_STRICT | MPM_FLAG_NAIVE)) != 0;
   if (multi) MPM_CUDA(cudaMemsetAsync(mig.count, 0, 8, stream));
+  if (multi && !fast2d() && resort_due) {  // paths without the on-the-fly variant re-sort stand-alone, now
+    int rc = rebin_storage();
+    if (rc) return rc;
+  }
   if (fused) {
     {
       Phase ph(this, MPM_PHASE_CLEAR, 0);
@@ -699,18 +733,18 @@ int mpm_handle::step_grid_g2p(float dt) {
     auto run_tail = [&]() {
       if (n <= n_binned) return;
       if (D == 2) {
-        launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
+        launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream, nullptr, dev_ext);
         GridPtrs<2> gn = gp<2>();
         gn.g = grid_next;
-        launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gn, status_dev, stream);
+        launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gn, status_dev, stream, dev_ext);
         if (resort)
           launch_reorder_scatter<2>(s2[cur], s2[cur ^ 1], n_binned, n, G.n_bins, bin_start_buf[bs ^ 1], sb.key[0],
-                                    (const unsigned *)sb.val[0], stream);
+                                    (const unsigned *)sb.val[0], stream, dev_ext);
       } else {
-        launch_g2p_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), mig, status_dev, strict, stream);
+        launch_g2p_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), mig, status_dev, strict, stream, nullptr, dev_ext);
         GridPtrs<3> gn = gp<3>();
         gn.g = grid_next;
-        launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gn, status_dev, stream);
+        launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gn, status_dev, stream, dev_ext);
       }
     };
     if (overlap && act_hi_begin > act_lo_end && D == 2) {
@@ -747,6 +781,8 @@ int mpm_handle::step_grid_g2p(float dt) {
       run_tail();
     }
     if (resort) {
+      if (multi)  // the new extent (dead slots dropped) = first slot of the "dead" bin of the new order
+        launch_slab_counters(dev_ext, nullptr, nullptr, nullptr, nullptr, 0, cap, bin_start_buf[bs ^ 1] + G.n_bins, stream);
       int rc = end_resort();
       if (rc) return rc;
     }
@@ -754,25 +790,51 @@ int mpm_handle::step_grid_g2p(float dt) {
     float4 *t = grid;
     grid = grid_next;
     grid_next = t;
-    p2g_ready = true;  // ... up to the immigrants, which mpm_step_immigrate adds
+    p2g_ready = true;  // ... up to migrating particles, which the x-slab exchange adds (slab_stage / slab_consume)
     p2g_dt = dt;
     if (prof_on) prof.fused_substeps++;
   } else {
-    Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
-    if (binned && (cfg.flags & MPM_FLAG_G2P_TILE)) {
-      if (D == 2) launch_g2p_bins<2>(P, G, dt, s2[cur], n_binned, bin_start, gp<2>(), mig, status_dev, strict, stream);
-      else launch_g2p_bins<3>(P, G, dt, s3[cur], n_binned, bin_start, gp<3>(), mig, status_dev, strict, stream);
-      if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream);
-      else launch_g2p_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), mig, status_dev, strict, stream);
-    } else {
-      if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), mig, status_dev, strict, stream, stats_dev);
-      else launch_g2p_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), mig, status_dev, strict, stream, stats_dev);
+    if (pipelined) {
+      Phase ph(this, MPM_PHASE_CLEAR, 0);
+      MPM_CUDA(cudaMemsetAsync(grid_next, 0, (size_t)nodes * sizeof(float4), stream));  // :50 of the next substep
     }
-    p2g_ready = false;
-  }
-  if (multi) {
-    MPM_CUDA(cudaMemcpyAsync(mig_count_host, mig.count, 8, cudaMemcpyDeviceToHost, stream));
-    mig_counts_valid = true;
+    {
+      Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
+      if (binned && (cfg.flags & MPM_FLAG_G2P_TILE)) {
+        if (D == 2) launch_g2p_bins<2>(P, G, dt, s2[cur], n_binned, bin_start, gp<2>(), mig, status_dev, strict, stream);
+        else launch_g2p_bins<3>(P, G, dt, s3[cur], n_binned, bin_start, gp<3>(), mig, status_dev, strict, stream);
+        if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], n_binned, n, gp<2>(), mig, status_dev, strict, stream, nullptr, dev_ext);
+        else launch_g2p_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), mig, status_dev, strict, stream, nullptr, dev_ext);
+      } else {
+        if (D == 2) launch_g2p_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), mig, status_dev, strict, stream, stats_dev, dev_ext);
+        else launch_g2p_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), mig, status_dev, strict, stream, stats_dev, dev_ext);
+      }
+    }
+    if (pipelined) {
+      // x-slab handles run every path on the pipelined schedule: the P2G of the NEXT substep follows at once
+      // (two kernels instead of the fused one), so that one exchange carries ghost sums and emigrants together
+      Phase ph(this, MPM_PHASE_P2G, n > 0 ? 1 : 0);
+      const bool strict_p2g = (cfg.flags & MPM_FLAG_STRICT) != 0;
+      if (D == 2) {
+        GridPtrs<2> gn = gp<2>();
+        gn.g = grid_next;
+        if (binned) launch_p2g_cells<2>(P, G, dt, s2[cur], n_binned, bin_start, gn, status_dev, stats_dev, strict_p2g, stream);
+        launch_p2g_naive<2>(P, dt, s2[cur], binned ? n_binned : 0, n, gn, status_dev, stream, dev_ext);
+      } else {
+        GridPtrs<3> gn = gp<3>();
+        gn.g = grid_next;
+        if (binned) launch_p2g_cells<3>(P, G, dt, s3[cur], n_binned, bin_start, gn, status_dev, stats_dev, strict_p2g, stream);
+        launch_p2g_naive<3>(P, dt, s3[cur], binned ? n_binned : 0, n, gn, status_dev, stream, dev_ext);
+      }
+      grid_read = grid;
+      float4 *t = grid;
+      grid = grid_next;
+      grid_next = t;
+      p2g_ready = true;
+      p2g_dt = dt;
+    } else {
+      p2g_ready = false;
+    }
   }
   if (prof_on) prof.substeps++;
   return MPM_OK;
@@ -890,6 +952,7 @@ int mpm_handle::poll_status() {
 
 long long mpm_handle::read_ids(void *aos_out, int *ids_out, long long max_n, int to_device) {
   join_side();
+  if (multi) sync_extent();
   if (max_n < n || !aos_out || !ids_out) {
     err = "read_ids: buffers must hold mpm_storage_extent() records";
     return MPM_E_INVALID;
@@ -913,86 +976,147 @@ long long mpm_handle::read_ids(void *aos_out, int *ids_out, long long max_n, int
   return n;
 }
 
-int mpm_handle::halo_add(int have_lo, int have_hi) {
-  if (!multi) return MPM_OK;
-  MPM_CUDA(cudaSetDevice(cfg.device));
-  Phase ph(this, MPM_PHASE_HALO, (have_lo ? 1 : 0) + (have_hi ? 1 : 0));
+// ------------------------------------------------------------------------------------------------
+// x-slab protocol: ONE fixed-size message per neighbour and substep, no host synchronisation.
+//
+// Invariant between substeps (pipelined schedule): the particles hold the state after G2P(n) and `grid` holds
+// this handle's partial sums of P2G(n+1).  A particle that changes slab in G2P(n) is packed into the message for
+// that neighbour; its P2G(n+1) share goes to the node columns this handle holds on THIS side (so the two shared
+// columns leave complete) and to the remaining columns on the receiver's side.  The message carries the partial
+// sums of the two shared node columns, the emigrant count and the records; the receiver adds the sums
+// (commutative: both sides end with bit-identical shared columns), appends the records behind its storage extent
+// -- which lives on the device, like the counts -- and scatters their remaining P2G share.
+//   slab_begin : (re)compute P2G of the resident particles, stage the messages              -> exchange
+//   slab_step  : [consume the received messages] grid update, G2P + next P2G, stage         -> exchange
+//   slab_settle: consume the received messages (state complete: every particle resident, grid whole)
+// ------------------------------------------------------------------------------------------------
+int mpm_handle::slab_stage() {
+  const bool have_lo = cfg.slab_lo > 0, have_hi = cfg.slab_hi < cfg.n_grid;
+  const int K = mig.cap;
+  // emigrants of this substep: their share of the NEXT P2G on the node columns this handle holds
+  if (p2g_ready) {
+    const int c0 = cfg.slab_lo, c1 = cfg.slab_lo + P.ncol;
+    if (D == 2) {
+      if (have_lo) launch_scatter_records<2>(P, p2g_dt, mig.send_lo, mig.count + 0, K, grid, c0, c1, status_dev, stream);
+      if (have_hi) launch_scatter_records<2>(P, p2g_dt, mig.send_hi, mig.count + 1, K, grid, c0, c1, status_dev, stream);
+    } else {
+      if (have_lo) launch_scatter_records<3>(P, p2g_dt, mig.send_lo, mig.count + 0, K, grid, c0, c1, status_dev, stream);
+      if (have_hi) launch_scatter_records<3>(P, p2g_dt, mig.send_hi, mig.count + 1, K, grid, c0, c1, status_dev, stream);
+    }
+  }
   const long long hn = halo_nodes();
-  if (have_lo) launch_halo_add(grid, halo_recv_lo, hn, stream);
-  if (have_hi) launch_halo_add(grid + (nodes - hn), halo_recv_hi, hn, stream);
+  if (have_lo) {
+    MPM_CUDA(cudaMemcpyAsync(msg_send[0], grid, msg_hdr, cudaMemcpyDeviceToDevice, stream));
+    MPM_CUDA(cudaMemcpyAsync(hdr(msg_send[0]), mig.count + 0, 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  if (have_hi) {
+    MPM_CUDA(cudaMemcpyAsync(msg_send[1], grid + (nodes - hn), msg_hdr, cudaMemcpyDeviceToDevice, stream));
+    MPM_CUDA(cudaMemcpyAsync(hdr(msg_send[1]), mig.count + 1, 4, cudaMemcpyDeviceToDevice, stream));
+  }
+  // the emigrants are no longer this handle's
+  launch_slab_counters(dev_ext, nullptr, nullptr, have_lo ? mig.count + 0 : nullptr, have_hi ? mig.count + 1 : nullptr, K,
+                       cap, nullptr, stream);
   MPM_CUDA(cudaGetLastError());
+  slab_state = SLAB_STAGED;
   return MPM_OK;
 }
 
-int mpm_handle::migration_describe(mpm_migration_desc *d) {
-  memset(d, 0, sizeof *d);
-  d->record_bytes = mig_words() * 4;
-  if (!multi) return MPM_OK;
-  MPM_CUDA(cudaSetDevice(cfg.device));
-  MPM_CUDA(cudaStreamSynchronize(stream));
-  if (mig_counts_valid) {  // emigrants of the last G2P leave this handle now
-    for (int k = 0; k < 2; k++) {
-      mig_sent[k] = mig_count_host[k] < mig.cap ? mig_count_host[k] : mig.cap;
-      live -= mig_sent[k];
-    }
-    mig_counts_valid = false;
+int mpm_handle::slab_consume() {
+  const bool have_lo = cfg.slab_lo > 0, have_hi = cfg.slab_hi < cfg.n_grid;
+  const int K = mig.cap;
+  const long long hn = halo_nodes();
+  {
+    Phase ph(this, MPM_PHASE_HALO, (have_lo ? 1 : 0) + (have_hi ? 1 : 0));
+    if (have_lo) launch_halo_add(grid, (const float4 *)msg_recv[0], hn, stream);
+    if (have_hi) launch_halo_add(grid + (nodes - hn), (const float4 *)msg_recv[1], hn, stream);
   }
-  d->send_lo = mig.send_lo;
-  d->send_hi = mig.send_hi;
-  d->n_send_lo = mig_sent[0];
-  d->n_send_hi = mig_sent[1];
-  d->recv_lo = mig_recv_lo;
-  d->recv_hi = mig_recv_hi;
-  d->recv_capacity = mig.cap;
-  return MPM_OK;
-}
-
-int mpm_handle::immigrate(long long n_lo, long long n_hi) {
-  if (!multi) return MPM_OK;
-  if (n_lo < 0 || n_hi < 0 || n_lo > mig.cap || n_hi > mig.cap) {
-    err = "immigrate: counts exceed the landing zones";
-    return MPM_E_INVALID;
-  }
-  MPM_CUDA(cudaSetDevice(cfg.device));
-  if (n + n_lo + n_hi > cap) {
-    // the storage extent still counts the slots of particles that emigrated since the last re-sort:
-    // compact them away before giving up (the senders have already handed these arrivals over)
-    if (live + n_lo + n_hi > cap) {
-      err = "immigrate: storage full (capacity must leave room for the immigrants)";
-      return MPM_E_CAPACITY;
-    }
-    int rc = rebin_storage();
+  // room for the arrivals?  `n` is the host's upper bound of the extent (it grows by K per neighbour and substep
+  // until a re-sort reads the exact value back); compact before it would pass the capacity
+  const long long room = (long long)K * ((have_lo ? 1 : 0) + (have_hi ? 1 : 0));
+  if (n + room > cap) {
+    int rc = sync_extent();  // the exact extent instead of the bound (small handles get here; big ones re-sort first)
     if (rc) return rc;
-    if (n + n_lo + n_hi > cap) {
-      err = "immigrate: storage full after compaction";
-      return MPM_E_CAPACITY;
+    if (n + room > cap && steps_since_sort > 0) {
+      rc = rebin_storage();  // drops the slots of emigrated particles
+      if (rc) return rc;
     }
   }
   {
-  Phase ph(this, MPM_PHASE_MIGRATE, (n_lo ? 1 : 0) + (n_hi ? 1 : 0));
-  if (D == 2) {
-    launch_immigrate<2>(mig_recv_lo, n_lo, s2[cur], n, stream);
-    launch_immigrate<2>(mig_recv_hi, n_hi, s2[cur], n + n_lo, stream);
-  } else {
-    launch_immigrate<3>(mig_recv_lo, n_lo, s3[cur], n, stream);
-    launch_immigrate<3>(mig_recv_hi, n_hi, s3[cur], n + n_lo, stream);
+    Phase ph(this, MPM_PHASE_MIGRATE, 3);
+    const float *r_lo = have_lo ? recs(msg_recv[0]) : nullptr, *r_hi = have_hi ? recs(msg_recv[1]) : nullptr;
+    const int *c_lo = have_lo ? hdr(msg_recv[0]) : nullptr, *c_hi = have_hi ? hdr(msg_recv[1]) : nullptr;
+    // arrivals from below were scattered into the shared columns lo, lo+1 by their sender; from above into hi, hi+1
+    const int lo = cfg.slab_lo, top = cfg.slab_lo + P.ncol;
+    if (D == 2) {
+      launch_immigrate<2>(r_lo, c_lo, r_hi, c_hi, K, s2[cur], dev_ext, cap, status_dev, stream);
+      if (have_lo) launch_scatter_records<2>(P, p2g_dt, r_lo, c_lo, K, grid, lo + 2, top, status_dev, stream);
+      if (have_hi) launch_scatter_records<2>(P, p2g_dt, r_hi, c_hi, K, grid, lo, top - 2, status_dev, stream);
+    } else {
+      launch_immigrate<3>(r_lo, c_lo, r_hi, c_hi, K, s3[cur], dev_ext, cap, status_dev, stream);
+      if (have_lo) launch_scatter_records<3>(P, p2g_dt, r_lo, c_lo, K, grid, lo + 2, top, status_dev, stream);
+      if (have_hi) launch_scatter_records<3>(P, p2g_dt, r_hi, c_hi, K, grid, lo, top - 2, status_dev, stream);
+    }
+    launch_slab_counters(dev_ext, c_lo, c_hi, nullptr, nullptr, K, cap, nullptr, stream);
   }
-  if (fused && p2g_ready && n_lo + n_hi > 0) {
-    // the grid already holds the next substep's P2G of everyone else: add the arrivals' share
-    if (D == 2) launch_p2g_naive<2>(P, p2g_dt, s2[cur], n, n + n_lo + n_hi, gp<2>(), status_dev, stream);
-    else launch_p2g_naive<3>(P, p2g_dt, s3[cur], n, n + n_lo + n_hi, gp<3>(), status_dev, stream);
-  }
-  }  // the re-sort below is timed under its own phase
-  n += n_lo + n_hi;
-  live += n_lo + n_hi;
-  mig_sent[0] = mig_sent[1] = 0;
-  steps_since_sort++;
-  const int every = current_interval();
-  if (every > 0 && steps_since_sort >= every) {
-    if (fast2d() && n > 0) resort_due = true;  // rides on the next substep kernel
-    else return rebin_storage();
-  }
+  n = n + room < cap ? n + room : cap;
   MPM_CUDA(cudaGetLastError());
+  return MPM_OK;
+}
+
+int mpm_handle::slab_begin(float dt) {
+  if (!multi) return 0;
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  if (p2g_ready && p2g_dt == dt && slab_state == SLAB_SETTLED) return 0;  // state complete, nothing to exchange
+  if (slab_state == SLAB_STAGED) {
+    err = "slab_begin: messages of the last substep are still outstanding (exchange them, then mpm_slab_settle)";
+    return MPM_E_STATE;
+  }
+  int rc = resident_p2g(dt);
+  if (rc) return rc;
+  MPM_CUDA(cudaMemsetAsync(mig.count, 0, 8, stream));  // nobody emigrates in a P2G
+  if ((rc = slab_stage())) return rc;
+  return 1;
+}
+
+int mpm_handle::slab_step(float dt) {
+  if (!multi) {
+    err = "slab_step: this handle owns the whole domain (use mpm_substep)";
+    return MPM_E_STATE;
+  }
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  if (slab_state == SLAB_FRESH || !p2g_ready || p2g_dt != dt) {
+    err = "slab_step: call mpm_slab_begin first (after an upload or a change of dt) and exchange its messages";
+    return MPM_E_STATE;
+  }
+  int rc;
+  if (slab_state == SLAB_STAGED)
+    if ((rc = slab_consume())) return rc;
+  const int every = current_interval();
+  if (every > 0 && steps_since_sort >= every) resort_due = true;  // consumed inside step_grid_g2p
+  if ((rc = step_grid_g2p(dt))) return rc;
+  steps_since_sort++;
+  return slab_stage();
+}
+
+int mpm_handle::slab_settle() {
+  if (!multi || slab_state != SLAB_STAGED) return MPM_OK;
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  int rc = slab_consume();
+  if (rc) return rc;
+  slab_state = SLAB_SETTLED;
+  return MPM_OK;
+}
+
+// exact storage extent / live count of an x-slab handle (they live on the device): synchronises
+int mpm_handle::sync_extent() {
+  if (!multi) return MPM_OK;
+  MPM_CUDA(cudaSetDevice(cfg.device));
+  join_side();
+  int e2[2] = {0, 0};
+  MPM_CUDA(cudaMemcpyAsync(e2, dev_ext, 8, cudaMemcpyDeviceToHost, stream));
+  MPM_CUDA(cudaStreamSynchronize(stream));
+  n = e2[0];
+  live = e2[1];
   return MPM_OK;
 }
 
@@ -1075,13 +1199,21 @@ int mpm_upload_particles_ids(mpm_handle *h, const void *aos, const int *ids, lon
 long long mpm_read_particles_ids(mpm_handle *h, void *aos_out, int *ids_out, long long max_n, int to_device) {
   return h ? h->read_ids(aos_out, ids_out, max_n, to_device) : MPM_E_INVALID;
 }
-long long mpm_storage_extent(const mpm_handle *h) { return h ? h->n : -1; }
+long long mpm_storage_extent(mpm_handle *h) {
+  if (!h) return -1;
+  if (h->sync_extent() != MPM_OK) return MPM_E_CUDA;
+  return h->n;
+}
 int mpm_substep(mpm_handle *h, float dt, int n_steps) { return h ? h->substep(dt, n_steps) : MPM_E_INVALID; }
 int mpm_read_particles(mpm_handle *h, void *aos_out, long long n, int to_device) {
   return h ? h->read(aos_out, n, to_device) : MPM_E_INVALID;
 }
 int mpm_read_grid(mpm_handle *h, int stage, float *out) { return h ? h->read_grid(stage, out) : MPM_E_INVALID; }
-long long mpm_particle_count(const mpm_handle *h) { return h ? h->live : -1; }
+long long mpm_particle_count(mpm_handle *h) {
+  if (!h) return -1;
+  if (h->sync_extent() != MPM_OK) return MPM_E_CUDA;
+  return h->live;
+}
 int mpm_resort(mpm_handle *h) {
   if (!h) return MPM_E_INVALID;
   cudaSetDevice(h->cfg.device);
@@ -1136,36 +1268,32 @@ int mpm_bin_particles(mpm_handle *h, int *cell, int *key, int *order, int *bin_s
   return h ? h->bin_particles(cell, key, order, bin_start) : MPM_E_INVALID;
 }
 
-// ---- x-slab phases -------------------------------------------------------------------------------
-int mpm_halo_describe(mpm_handle *h, mpm_halo_desc *d) {
+// ---- x-slab protocol ------------------------------------------------------------------------------
+int mpm_slab_describe(mpm_handle *h, mpm_slab_desc *d) {
   if (!h || !d) return MPM_E_INVALID;
   memset(d, 0, sizeof *d);
   if (!h->multi) return MPM_OK;
-  const long long hn = h->halo_nodes();
-  d->send_lo = h->halo_send_lo;
-  d->send_hi = h->halo_send_hi;
-  d->recv_lo = h->halo_recv_lo;
-  d->recv_hi = h->halo_recv_hi;
-  d->bytes = hn * (long long)sizeof(float4);
+  d->send_lo = h->msg_send[0];
+  d->send_hi = h->msg_send[1];
+  d->recv_lo = h->msg_recv[0];
+  d->recv_hi = h->msg_recv[1];
+  d->bytes = (long long)h->msg_bytes;
+  d->halo_bytes = (long long)h->msg_hdr;
+  d->record_bytes = h->mig_words() * 4;
+  d->record_capacity = h->mig.cap;
+  d->has_lo = h->cfg.slab_lo > 0;
+  d->has_hi = h->cfg.slab_hi < h->cfg.n_grid;
   return MPM_OK;
 }
-int mpm_step_p2g(mpm_handle *h, float dt) {
+int mpm_slab_begin(mpm_handle *h, float dt) {
   if (!h) return MPM_E_INVALID;
-  cudaSetDevice(h->cfg.device);
   if (!(dt > 0)) dt = h->cfg.dt;
-  return h->step_p2g(dt);
+  return h->slab_begin(dt);
 }
-int mpm_step_halo_add(mpm_handle *h, int have_lo, int have_hi) { return h ? h->halo_add(have_lo, have_hi) : MPM_E_INVALID; }
-int mpm_step_grid_g2p(mpm_handle *h, float dt) {
+int mpm_slab_step(mpm_handle *h, float dt) {
   if (!h) return MPM_E_INVALID;
-  cudaSetDevice(h->cfg.device);
   if (!(dt > 0)) dt = h->cfg.dt;
-  return h->step_grid_g2p(dt);
+  return h->slab_step(dt);
 }
-int mpm_migration_describe(mpm_handle *h, mpm_migration_desc *d) {
-  return (h && d) ? h->migration_describe(d) : MPM_E_INVALID;
-}
-int mpm_step_immigrate(mpm_handle *h, long long n_lo, long long n_hi) {
-  return h ? h->immigrate(n_lo, n_hi) : MPM_E_INVALID;
-}
+int mpm_slab_settle(mpm_handle *h) { return h ? h->slab_settle() : MPM_E_INVALID; }
 }

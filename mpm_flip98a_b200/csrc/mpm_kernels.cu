@@ -53,10 +53,14 @@ template void launch_grid_update<3>(const Params &, float, GridPtrs<3>, cudaStre
 // ------------------------------------------------------------------------------------------------
 // naive P2G: one thread per particle, 3^D vector REDs (RED.E.ADD.F32x4) into L2.
 // ------------------------------------------------------------------------------------------------
+// dev_n (x-slab handles): the exact storage extent lives on the device (immigrants are appended without the host
+// learning their number); the host launches over an upper bound and the kernels stop at *dev_n
 template <int D, bool MIG>
 __global__ void __launch_bounds__(128) k_p2g_naive(Params P, float dt, SoA<D> s, long long first, long long n,
-                                                   float4 *__restrict__ grid, int *__restrict__ status) {
+                                                   float4 *__restrict__ grid, int *__restrict__ status,
+                                                   const int *__restrict__ dev_n) {
   long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (MIG && dev_n && n > *dev_n) n = *dev_n;
   if (i >= n) return;
   PState<D> p;
   load_full(s, i, p);
@@ -85,16 +89,16 @@ __global__ void __launch_bounds__(128) k_p2g_naive(Params P, float dt, SoA<D> s,
 
 template <int D>
 void launch_p2g_naive(const Params &P, float dt, const SoA<D> &s, long long first, long long n, GridPtrs<D> g,
-                      int *status, cudaStream_t st) {
+                      int *status, cudaStream_t st, const int *dev_n) {
   if (n - first <= 0) return;
   unsigned blocks = (unsigned)((n - first + 127) / 128);
-  if (P.multi) k_p2g_naive<D, true><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, status);
-  else k_p2g_naive<D, false><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, status);
+  if (P.multi) k_p2g_naive<D, true><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, status, dev_n);
+  else k_p2g_naive<D, false><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, status, nullptr);
 }
 template void launch_p2g_naive<2>(const Params &, float, const SoA<2> &, long long, long long, GridPtrs<2>, int *,
-                                  cudaStream_t);
+                                  cudaStream_t, const int *);
 template void launch_p2g_naive<3>(const Params &, float, const SoA<3> &, long long, long long, GridPtrs<3>, int *,
-                                  cudaStream_t);
+                                  cudaStream_t, const int *);
 
 // ------------------------------------------------------------------------------------------------
 // G2P building blocks (used by the G2P kernels below and by the fused G2P->P2G kernel)
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
       int bad = clamp_base<D>(P, st.base);
       if (bad) atomicOr(status, bad);
       const Material &mat = P.mat[material_index(P, p.mat)];
-      Mat<D> affine = p2g_affine<D, FAST>(P, mat, dt, p.F, p.C, p.Jp);  // FAST: Newton polar in 3D (mpm_math.cuh)
+      Mat<D> affine = p2g_affine<D>(P, mat, dt, p.F, p.C, p.Jp);
       float mv[D];
 #pragma unroll
       for (int c = 0; c < D; c++) mv[c] = P.mass_p * p.v[c];
@@ -642,8 +646,9 @@ template <int D, bool MIG, bool FAST, bool FLIP>
 __global__ void __launch_bounds__(128) k_g2p_naive(Params P, float dt, SoA<D> s, long long first, long long n,
                                                    const float4 *__restrict__ grid, const void *__restrict__ vold_,
                                                    MigPtrs mig, int *__restrict__ status,
-                                                   unsigned long long *__restrict__ stats) {
+                                                   unsigned long long *__restrict__ stats, const int *__restrict__ dev_n) {
   long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (MIG && dev_n && n > *dev_n) n = *dev_n;
   float disp = 0.0f;
   if (i < n) {
     GlobalFetch<D> fetch{grid, vold_};
@@ -789,14 +794,14 @@ template void launch_g2p_bins<3>(const Params &, const BinGeom &, float, const S
 
 template <int D>
 void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long first, long long n, GridPtrs<D> g,
-                      MigPtrs mig, int *status, bool strict, cudaStream_t st, unsigned long long *stats) {
+                      MigPtrs mig, int *status, bool strict, cudaStream_t st, unsigned long long *stats, const int *dev_n) {
   if (n - first <= 0) return;
   unsigned blocks = (unsigned)((n - first + 127) / 128);
   const bool flip = P.alpha != 0.0f;
 #define MPM_G2P_NAIVE(MIG_, FAST_)                                                                               \
   {                                                                                                              \
-    if (flip) k_g2p_naive<D, MIG_, FAST_, true><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status, stats); \
-    else k_g2p_naive<D, MIG_, FAST_, false><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status, stats);     \
+    if (flip) k_g2p_naive<D, MIG_, FAST_, true><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status, stats, dev_n); \
+    else k_g2p_naive<D, MIG_, FAST_, false><<<blocks, 128, 0, st>>>(P, dt, s, first, n, g.g, g.vold, mig, status, stats, dev_n);     \
   }
   if (mig.enabled) {
     if (strict) MPM_G2P_NAIVE(true, false)
@@ -808,9 +813,9 @@ void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long firs
 #undef MPM_G2P_NAIVE
 }
 template void launch_g2p_naive<2>(const Params &, float, const SoA<2> &, long long, long long, GridPtrs<2>, MigPtrs,
-                                  int *, bool, cudaStream_t, unsigned long long *);
+                                  int *, bool, cudaStream_t, unsigned long long *, const int *);
 template void launch_g2p_naive<3>(const Params &, float, const SoA<3> &, long long, long long, GridPtrs<3>, MigPtrs,
-                                  int *, bool, cudaStream_t, unsigned long long *);
+                                  int *, bool, cudaStream_t, unsigned long long *, const int *);
 
 // ------------------------------------------------------------------------------------------------
 // x-slab exchange helpers: ghost-column sum, immigrant unpack
@@ -828,12 +833,8 @@ void launch_halo_add(float4 *dst, const float4 *src, long long count, cudaStream
 }
 
 template <int D>
-__global__ void k_immigrate(const float *__restrict__ recv, long long count, SoA<D> s, long long first) {
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= count) return;
+__device__ __forceinline__ void unpack_mig_record(const float *__restrict__ r, PState<D> &p, int &id) {
   constexpr int W = MigRec<D>::WORDS;
-  const float *r = recv + t * W;
-  PState<D> p;
 #pragma unroll
   for (int c = 0; c < D; c++) {
     p.x[c] = r[c];
@@ -848,16 +849,108 @@ __global__ void k_immigrate(const float *__restrict__ recv, long long count, SoA
     }
   p.Jp = r[2 * D + 2 * D * D];
   p.mat = __float_as_int(r[2 * D + 2 * D * D + 1]);
-  store_state(s, first + t, p);
-  store_tags(s, first + t, p.mat, __float_as_int(r[W - 2]));
+  id = __float_as_int(r[W - 2]);
 }
+
+// Arrivals of one exchange: the records of both neighbours' messages are appended behind the current storage extent.
+// Their number is only known on the device (message headers), so is the extent (*ext); threads [0,K) serve the
+// lower neighbour's message, [K,2K) the upper one's.
 template <int D>
-void launch_immigrate(const float *recv, long long count, const SoA<D> &s, long long first, cudaStream_t st) {
-  if (count <= 0) return;
-  k_immigrate<D><<<(unsigned)((count + 255) / 256), 256, 0, st>>>(recv, count, s, first);
+__global__ void k_immigrate(const float *__restrict__ recv_lo, const int *__restrict__ cnt_lo, const float *__restrict__ recv_hi,
+                            const int *__restrict__ cnt_hi, int K, SoA<D> s, const int *__restrict__ ext, long long cap,
+                            int *__restrict__ status) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int side = t >= K ? 1 : 0, idx = t - side * K;
+  const int n_lo = cnt_lo ? min(*cnt_lo, K) : 0, n_hi = cnt_hi ? min(*cnt_hi, K) : 0;
+  if (idx >= (side ? n_hi : n_lo)) return;
+  const long long slot = (long long)ext[0] + (side ? n_lo : 0) + idx;
+  if (slot >= cap) {
+    atomicOr(status, STATUS_MIGRATION_OVERFLOW);  // no room: the particle is lost and the run is flagged
+    return;
+  }
+  PState<D> p;
+  int id;
+  unpack_mig_record<D>((side ? recv_hi : recv_lo) + (size_t)idx * MigRec<D>::WORDS, p, id);
+  store_state(s, slot, p);
+  store_tags(s, slot, p.mat, id);
 }
-template void launch_immigrate<2>(const float *, long long, const SoA<2> &, long long, cudaStream_t);
-template void launch_immigrate<3>(const float *, long long, const SoA<3> &, long long, cudaStream_t);
+
+// P2G share of the particles in a migration message, restricted to the node columns [col_lo, col_hi): a particle
+// that changes slab contributes to the shared columns on the SENDER's side (before its partial sums leave) and to
+// the remaining columns on the RECEIVER's side, so one exchange per substep carries ghost sums and emigrants together.
+// Exact association (:92-100); dt = the substep the scatter belongs to.
+template <int D>
+__global__ void k_scatter_records(Params P, float dt, const float *__restrict__ recs, const int *__restrict__ cnt, int K,
+                                  float4 *__restrict__ grid, int col_lo, int col_hi, int *__restrict__ status) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= min(*cnt, K)) return;
+  PState<D> p;
+  int id;
+  unpack_mig_record<D>(recs + (size_t)t * MigRec<D>::WORDS, p, id);
+  Stencil<D> st = make_stencil<D>(p.x, P.inv_dx);
+  bool bad = false;
+#pragma unroll
+  for (int k = 0; k < D; k++) {  // global clamp only: the base column of such a particle lies outside one of the two slabs
+    if (st.base[k] < 0) { st.base[k] = 0; bad = true; }
+    if (st.base[k] > P.n_grid - 2) { st.base[k] = P.n_grid - 2; bad = true; }
+  }
+  if (bad) atomicOr(status, STATUS_DOMAIN);
+  const Material &mat = P.mat[material_index(P, p.mat)];
+  const Mat<D> affine = p2g_affine<D>(P, mat, dt, p.F, p.C, p.Jp);
+  float mv[D];
+#pragma unroll
+  for (int c = 0; c < D; c++) mv[c] = P.mass_p * p.v[c];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const int col = st.base[0] + a;
+    if (col < col_lo || col >= col_hi) continue;
+#pragma unroll
+    for (int b = 0; b < 3; b++)
+#pragma unroll
+      for (int c = 0; c < (D == 3 ? 3 : 1); c++) {
+        float nv[D + 1];
+        p2g_node_value<D>(P, st, affine, mv, a, b, c, nv);
+        red_node<D>(P, grid, col, st.base[1] + b, D == 3 ? st.base[D - 1] + c : 0, nv);
+      }
+  }
+}
+
+// extent / live-count bookkeeping of an x-slab handle, on the device: ext[0] = storage extent, ext[1] = live particles
+__global__ void k_slab_counters(int *ext, const int *add_a, const int *add_b, const int *sub_a, const int *sub_b, int K,
+                                long long cap, const int *set_extent) {
+  if (threadIdx.x || blockIdx.x) return;
+  int add = (add_a ? min(*add_a, K) : 0) + (add_b ? min(*add_b, K) : 0);
+  int sub = (sub_a ? min(*sub_a, K) : 0) + (sub_b ? min(*sub_b, K) : 0);
+  if (set_extent) ext[0] = *set_extent;
+  long long e = (long long)ext[0] + add;
+  ext[0] = (int)(e < cap ? e : cap);
+  ext[1] += add - sub;
+}
+
+template <int D>
+void launch_immigrate(const float *recv_lo, const int *cnt_lo, const float *recv_hi, const int *cnt_hi, int K,
+                      const SoA<D> &s, const int *ext, long long cap, int *status, cudaStream_t st) {
+  if (K <= 0 || (!cnt_lo && !cnt_hi)) return;
+  k_immigrate<D><<<(unsigned)((2 * K + 255) / 256), 256, 0, st>>>(recv_lo, cnt_lo, recv_hi, cnt_hi, K, s, ext, cap, status);
+}
+template void launch_immigrate<2>(const float *, const int *, const float *, const int *, int, const SoA<2> &, const int *,
+                                  long long, int *, cudaStream_t);
+template void launch_immigrate<3>(const float *, const int *, const float *, const int *, int, const SoA<3> &, const int *,
+                                  long long, int *, cudaStream_t);
+template <int D>
+void launch_scatter_records(const Params &P, float dt, const float *recs, const int *cnt, int K, float4 *grid, int col_lo,
+                            int col_hi, int *status, cudaStream_t st) {
+  if (K <= 0 || !cnt || col_lo >= col_hi) return;
+  k_scatter_records<D><<<(unsigned)((K + 127) / 128), 128, 0, st>>>(P, dt, recs, cnt, K, grid, col_lo, col_hi, status);
+}
+template void launch_scatter_records<2>(const Params &, float, const float *, const int *, int, float4 *, int, int, int *,
+                                        cudaStream_t);
+template void launch_scatter_records<3>(const Params &, float, const float *, const int *, int, float4 *, int, int, int *,
+                                        cudaStream_t);
+void launch_slab_counters(int *ext, const int *add_a, const int *add_b, const int *sub_a, const int *sub_b, int K,
+                          long long cap, const int *set_extent, cudaStream_t st) {
+  k_slab_counters<<<1, 32, 0, st>>>(ext, add_a, add_b, sub_a, sub_b, K, cap, set_extent);
+}
 
 // ------------------------------------------------------------------------------------------------
 // AoS (the reference's Particle record, :28-42: x v F C Jp c) <-> SoA

@@ -24,14 +24,22 @@ struct GridPtrs {
 // ---- naive path: one thread per particle, vector REDs straight into L2 -------------------------
 template <int D>
 void launch_p2g_naive(const Params &P, float dt, const SoA<D> &s, long long first, long long n, GridPtrs<D> g,
-                      int *status, cudaStream_t st);
+                      int *status, cudaStream_t st, const int *dev_n = nullptr);
 template <int D>
 void launch_g2p_naive(const Params &P, float dt, const SoA<D> &s, long long first, long long n, GridPtrs<D> g,
-                      MigPtrs mig, int *status, bool strict, cudaStream_t st, unsigned long long *stats = nullptr);
+                      MigPtrs mig, int *status, bool strict, cudaStream_t st, unsigned long long *stats = nullptr,
+                      const int *dev_n = nullptr);
 // x-slab exchange helpers
 void launch_halo_add(float4 *dst, const float4 *src, long long count, cudaStream_t st);
+// message-driven immigration and the restricted P2G share of migrating particles (see mpm_kernels.cu)
 template <int D>
-void launch_immigrate(const float *recv, long long count, const SoA<D> &s, long long first, cudaStream_t st);
+void launch_immigrate(const float *recv_lo, const int *cnt_lo, const float *recv_hi, const int *cnt_hi, int K,
+                      const SoA<D> &s, const int *ext, long long cap, int *status, cudaStream_t st);
+template <int D>
+void launch_scatter_records(const Params &P, float dt, const float *recs, const int *cnt, int K, float4 *grid, int col_lo,
+                            int col_hi, int *status, cudaStream_t st);
+void launch_slab_counters(int *ext, const int *add_a, const int *add_b, const int *sub_a, const int *sub_b, int K,
+                          long long cap, const int *set_extent, cudaStream_t st);
 template <int D>
 void launch_grid_update(const Params &P, float dt, GridPtrs<D> g, cudaStream_t st);
 
@@ -104,10 +112,11 @@ int radix_sort_pairs(SortBuffers &B, long long n, int bits, cudaStream_t st);
 // storage re-sort by counting (see mpm_sort.cu): counts[n_bins+2] zeroed by the caller and scanned afterwards
 template <int D>
 void launch_count_rank(const Params &P, const BinGeom &G, const SoA<D> &s, long long n, unsigned *counts, unsigned *key,
-                       unsigned *rank, int *status, cudaStream_t st);
+                       unsigned *rank, int *status, cudaStream_t st, const int *dev_n = nullptr);
 template <int D>
 void launch_reorder_scatter(const SoA<D> &src, const SoA<D> &dst, long long first, long long n, int n_bins,
-                            const int *start, const unsigned *key, const unsigned *rank, cudaStream_t st);
+                            const int *start, const unsigned *key, const unsigned *rank, cudaStream_t st,
+                            const int *dev_n = nullptr);
 // bin_start[n_bins+1] from sorted keys
 void launch_bin_starts(const unsigned *sorted_key, long long n, int n_bins, int *bin_start, cudaStream_t st);
 void launch_iota(int *v, long long n, cudaStream_t st);

@@ -283,21 +283,21 @@ MPM_HD Mat<2> rotation_of(const Mat<2> &F) {
   polar2(F, r, s);
   return r;
 }
-MPM_HD Mat<3> rotation_of(const Mat<3> &F) {
+MPM_HD Mat<3> rotation_of_svd(const Mat<3> &F) {
   Mat<3> U, V;
   float sg[3];
   svd3(F, U, sg, V);
   return mat_mul<3>(U, mat_transposed<3>(V));
 }
 
-// Fast rotation factor for the 3D stress (MPM_FLAG_STRICT and the naive path keep rotation_of): Newton's
-// iteration for the polar decomposition, X <- (X + X^-T) / 2 from X0 = F, converges quadratically to the
-// rotation R of F = R S.  |X_{k+1} - X_k| <= 2e-4 means X_{k+1} is within ~2e-8 of R (below fp32 rounding):
-// 2-3 iterations for snow (F within 2.5 % of a rotation after the plastic clamp), 4-6 for a jelly under load,
-// ~70 instructions each -- against ~1500 for the 4-sweep Jacobi SVD whose U V^T it replaces (agreement
-// ~1e-7, tests/test_host_math.py::test_polar3_newton_matches_svd_rotation).  Near-singular or inverted F
-// (det <= 1e-6 |F|^3) falls back to the SVD.
-MPM_HD Mat<3> rotation_of_fast(const Mat<3> &F) {
+// Rotation factor for the 3D stress (the 3D lift has no counterpart in the reference; the CPU oracle defines it with
+// the very same statements, oracle/mpm_oracle.cpp rotation3): Newton's iteration for the polar decomposition,
+// X <- (X + X^-T) / 2 from X0 = F, converges quadratically to the rotation R of F = R S.  |X_{k+1} - X_k| <= 2e-4
+// means X_{k+1} is within ~2e-8 of R (below fp32 rounding): 2-3 iterations for snow (F within 2.5 % of a rotation
+// after the plastic clamp), 4-6 for a jelly under load, ~70 instructions each -- against ~1500 for the 4-sweep Jacobi
+// SVD whose U V^T it replaced in round 2 (the two agree to ~1e-6, tests/test_host_math.py).  Near-singular or
+// inverted F (det <= 1e-6 |F|^3) takes the SVD's U V^T.
+MPM_HD Mat<3> rotation_of(const Mat<3> &F) {
   Mat<3> X = F;
   float scale = 0.0f;
 #pragma unroll
@@ -312,7 +312,7 @@ MPM_HD Mat<3> rotation_of_fast(const Mat<3> &F) {
     K.d[1][0] = c[1] * a[2] - c[2] * a[1]; K.d[1][1] = c[2] * a[0] - c[0] * a[2]; K.d[1][2] = c[0] * a[1] - c[1] * a[0];
     K.d[2][0] = a[1] * b[2] - a[2] * b[1]; K.d[2][1] = a[2] * b[0] - a[0] * b[2]; K.d[2][2] = a[0] * b[1] - a[1] * b[0];
     const float det = a[0] * K.d[0][0] + a[1] * K.d[0][1] + a[2] * K.d[0][2];
-    if (!(det > 1e-6f * scale * scale * scale)) return rotation_of(F);
+    if (!(det > 1e-6f * scale * scale * scale)) return rotation_of_svd(F);
     const float h = 0.5f / det;
     float delta = 0.0f;
 #pragma unroll
@@ -327,7 +327,7 @@ MPM_HD Mat<3> rotation_of_fast(const Mat<3> &F) {
   }
   return X;
 }
-MPM_HD Mat<2> rotation_of_fast(const Mat<2> &F) { return rotation_of(F); }
+
 
 // ---------------------------------------------------------------------------------------------
 // Base cell + quadratic B-spline weights, :55-64.  The cast is C++ truncation (taichi.h:7185),
@@ -370,7 +370,7 @@ MPM_HD int material_index(const Params &P, int c) {
 
 // :67-89 -- the matrix `affine` such that the node contribution is
 //   w * ( (mass_p * v, mass_p) + (affine * dpos, 0) ),  dpos = (node_offset - fx) * dx
-template <int D, bool FASTROT = false>
+template <int D>
 MPM_HD Mat<D> p2g_affine(const Params &P, const Material &mat, float dt, const Mat<D> &F, const Mat<D> &C, float Jp) {
   float e;
   if (mat.kind == KIND_SNOW) e = expf(mat.hardening * (1.0f - Jp));  // :67
@@ -384,7 +384,7 @@ MPM_HD Mat<D> p2g_affine(const Params &P, const Material &mat, float dt, const M
   if (mat.kind == KIND_FLUID) {
     PF = mat_diag<D>(lambda * (J - 1) * J);
   } else {
-    Mat<D> r = FASTROT ? rotation_of_fast(F) : rotation_of(F);  // :75-76
+    Mat<D> r = rotation_of(F);  // :75-76
     PF = mat_add<D>(mat_mul<D>(mat_scale<D>(2 * mu, mat_sub<D>(F, r)), mat_transposed<D>(F)),
                     mat_diag<D>(lambda * (J - 1) * J));  // :81
   }

@@ -260,8 +260,9 @@ void launch_active_bins(const int *bin_start, int n_bins, unsigned *offs, unsign
 template <int D>
 __global__ void __launch_bounds__(256) k_count_rank(Params P, BinGeom G, SoA<D> s, long long n, unsigned *__restrict__ counts,
                                                     unsigned *__restrict__ key_out, unsigned *__restrict__ rank_out,
-                                                    int *__restrict__ status) {
+                                                    int *__restrict__ status, const int *__restrict__ dev_n) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (dev_n && n > *dev_n) n = *dev_n;  // x-slab handles: exact extent on the device
   const bool valid = i < n;
   unsigned kk = 0xffffffffu;
   if (valid) {
@@ -291,21 +292,22 @@ __global__ void __launch_bounds__(256) k_count_rank(Params P, BinGeom G, SoA<D> 
 }
 template <int D>
 void launch_count_rank(const Params &P, const BinGeom &G, const SoA<D> &s, long long n, unsigned *counts, unsigned *key,
-                       unsigned *rank, int *status, cudaStream_t st) {
+                       unsigned *rank, int *status, cudaStream_t st, const int *dev_n) {
   if (n <= 0) return;
-  k_count_rank<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, G, s, n, counts, key, rank, status);
+  k_count_rank<D><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P, G, s, n, counts, key, rank, status, dev_n);
 }
 template void launch_count_rank<2>(const Params &, const BinGeom &, const SoA<2> &, long long, unsigned *, unsigned *,
-                                   unsigned *, int *, cudaStream_t);
+                                   unsigned *, int *, cudaStream_t, const int *);
 template void launch_count_rank<3>(const Params &, const BinGeom &, const SoA<3> &, long long, unsigned *, unsigned *,
-                                   unsigned *, int *, cudaStream_t);
+                                   unsigned *, int *, cudaStream_t, const int *);
 
 // slots [first, n) of `src` -> dst[start[key] + rank]; dead slots (key == n_bins) are dropped
 template <int D>
 __global__ void __launch_bounds__(256) k_reorder_scatter(SoA<D> src, SoA<D> dst, long long first, long long n, int n_bins,
                                                          const int *__restrict__ start, const unsigned *__restrict__ key,
-                                                         const unsigned *__restrict__ rank) {
+                                                         const unsigned *__restrict__ rank, const int *__restrict__ dev_n) {
   const long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (dev_n && n > *dev_n) n = *dev_n;
   if (i >= n) return;
   const unsigned kk = key[i];
   if (kk >= (unsigned)n_bins) return;
@@ -317,14 +319,15 @@ __global__ void __launch_bounds__(256) k_reorder_scatter(SoA<D> src, SoA<D> dst,
 }
 template <int D>
 void launch_reorder_scatter(const SoA<D> &src, const SoA<D> &dst, long long first, long long n, int n_bins,
-                            const int *start, const unsigned *key, const unsigned *rank, cudaStream_t st) {
+                            const int *start, const unsigned *key, const unsigned *rank, cudaStream_t st, const int *dev_n) {
   if (n - first <= 0) return;
-  k_reorder_scatter<D><<<(unsigned)((n - first + 255) / 256), 256, 0, st>>>(src, dst, first, n, n_bins, start, key, rank);
+  k_reorder_scatter<D><<<(unsigned)((n - first + 255) / 256), 256, 0, st>>>(src, dst, first, n, n_bins, start, key, rank,
+                                                                            dev_n);
 }
 template void launch_reorder_scatter<2>(const SoA<2> &, const SoA<2> &, long long, long long, int, const int *,
-                                        const unsigned *, const unsigned *, cudaStream_t);
+                                        const unsigned *, const unsigned *, cudaStream_t, const int *);
 template void launch_reorder_scatter<3>(const SoA<3> &, const SoA<3> &, long long, long long, int, const int *,
-                                        const unsigned *, const unsigned *, cudaStream_t);
+                                        const unsigned *, const unsigned *, cudaStream_t, const int *);
 
 __global__ void k_iota(int *v, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

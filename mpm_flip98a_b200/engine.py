@@ -47,15 +47,11 @@ class Config(ctypes.Structure):
                 ("reserved", ctypes.c_int * 6)]
 
 
-class HaloDesc(ctypes.Structure):
+class SlabDesc(ctypes.Structure):
     _fields_ = [("send_lo", ctypes.c_void_p), ("send_hi", ctypes.c_void_p), ("recv_lo", ctypes.c_void_p),
-                ("recv_hi", ctypes.c_void_p), ("bytes", ctypes.c_longlong)]
-
-
-class MigrationDesc(ctypes.Structure):
-    _fields_ = [("send_lo", ctypes.c_void_p), ("send_hi", ctypes.c_void_p), ("n_send_lo", ctypes.c_longlong),
-                ("n_send_hi", ctypes.c_longlong), ("recv_lo", ctypes.c_void_p), ("recv_hi", ctypes.c_void_p),
-                ("recv_capacity", ctypes.c_longlong), ("record_bytes", ctypes.c_int)]
+                ("recv_hi", ctypes.c_void_p), ("bytes", ctypes.c_longlong), ("halo_bytes", ctypes.c_longlong),
+                ("record_bytes", ctypes.c_int), ("record_capacity", ctypes.c_int), ("has_lo", ctypes.c_int),
+                ("has_hi", ctypes.c_int)]
 
 
 class Profile(ctypes.Structure):
@@ -89,12 +85,20 @@ SYMBOLS = {
     "mpm_profile_enable": (ctypes.c_int, [_H, ctypes.c_int]),
     "mpm_profile_read": (ctypes.c_int, [_H, ctypes.POINTER(Profile)]),
     "mpm_bin_particles": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]),
-    "mpm_halo_describe": (ctypes.c_int, [_H, ctypes.POINTER(HaloDesc)]),
-    "mpm_step_p2g": (ctypes.c_int, [_H, ctypes.c_float]),
-    "mpm_step_halo_add": (ctypes.c_int, [_H, ctypes.c_int, ctypes.c_int]),
-    "mpm_step_grid_g2p": (ctypes.c_int, [_H, ctypes.c_float]),
-    "mpm_migration_describe": (ctypes.c_int, [_H, ctypes.POINTER(MigrationDesc)]),
-    "mpm_step_immigrate": (ctypes.c_int, [_H, ctypes.c_longlong, ctypes.c_longlong]),
+    "mpm_slab_describe": (ctypes.c_int, [_H, ctypes.POINTER(SlabDesc)]),
+    "mpm_slab_begin": (ctypes.c_int, [_H, ctypes.c_float]),
+    "mpm_slab_step": (ctypes.c_int, [_H, ctypes.c_float]),
+    "mpm_slab_settle": (ctypes.c_int, [_H]),
+    "mpm_group_create": (_H, [ctypes.POINTER(Config), ctypes.POINTER(ctypes.c_int), ctypes.c_int]),
+    "mpm_group_destroy": (None, [_H]),
+    "mpm_group_last_error": (ctypes.c_char_p, [_H]),
+    "mpm_group_upload_particles": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_longlong]),
+    "mpm_group_substep": (ctypes.c_int, [_H, ctypes.c_float, ctypes.c_int]),
+    "mpm_group_synchronize": (ctypes.c_int, [_H]),
+    "mpm_group_read_particles": (ctypes.c_int, [_H, ctypes.c_void_p, ctypes.c_longlong]),
+    "mpm_group_poll_status": (ctypes.c_int, [_H]),
+    "mpm_group_slab": (ctypes.c_int, [_H, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                      ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_longlong)]),
 }
 
 _lib = None
@@ -215,27 +219,20 @@ class Engine:
         keep = ids[:got] >= 0
         return out[:got][keep], ids[:got][keep]
 
-    def halo(self):
-        d = HaloDesc()
-        self._check(self.lib.mpm_halo_describe(self.h, ctypes.byref(d)))
+    def slab(self):
+        d = SlabDesc()
+        self._check(self.lib.mpm_slab_describe(self.h, ctypes.byref(d)))
         return d
 
-    def migration(self):
-        d = MigrationDesc()
-        self._check(self.lib.mpm_migration_describe(self.h, ctypes.byref(d)))
-        return d
+    def slab_begin(self, dt=0.0):
+        """P2G of the resident particles + staged messages; True when the caller must exchange them."""
+        return self._check(self.lib.mpm_slab_begin(self.h, dt)) == 1
 
-    def step_p2g(self, dt=0.0):
-        self._check(self.lib.mpm_step_p2g(self.h, dt))
+    def slab_step(self, dt=0.0):
+        self._check(self.lib.mpm_slab_step(self.h, dt))
 
-    def step_halo_add(self, have_lo, have_hi):
-        self._check(self.lib.mpm_step_halo_add(self.h, int(have_lo), int(have_hi)))
-
-    def step_grid_g2p(self, dt=0.0):
-        self._check(self.lib.mpm_step_grid_g2p(self.h, dt))
-
-    def step_immigrate(self, n_lo, n_hi):
-        self._check(self.lib.mpm_step_immigrate(self.h, n_lo, n_hi))
+    def slab_settle(self):
+        self._check(self.lib.mpm_slab_settle(self.h))
 
     def upload_device(self, dev_ptr, n):
         self._check(self.lib.mpm_upload_particles(self.h, dev_ptr, n, 1))
@@ -302,3 +299,68 @@ class Engine:
         n_bins = self._check(self.lib.mpm_bin_particles(self.h, cell.ctypes.data if want_cell else None,
                                                         key.ctypes.data, order.ctypes.data, start.ctypes.data))
         return cell, key, order, start[:n_bins + 1]
+
+
+class Group:
+    """Several GPUs behind one handle (include/mpm.h, mpm_group_*): `devices` lists one CUDA ordinal per x-slab."""
+
+    def __init__(self, devices, dim=2, n_grid=80, capacity=1 << 20, dt=None, vol_p=None, alpha=0.0, flags=0,
+                 rebin_every=0):
+        self.lib = load_library()
+        c = default_config(dim)
+        c.n_grid, c.capacity, c.alpha, c.flags, c.rebin_every = n_grid, capacity, alpha, flags, rebin_every
+        if dt is not None:
+            c.dt = dt
+        if vol_p is not None:
+            c.vol_p = vol_p
+        self.cfg, self.dim, self.words = c, dim, 2 * dim + 2 * dim * dim + 2
+        arr = (ctypes.c_int * len(devices))(*devices)
+        self.n_slabs = len(devices)
+        self.g = self.lib.mpm_group_create(ctypes.byref(c), arr, len(devices))
+        if not self.g:
+            raise MpmError(-1, "mpm_group_create")
+        self.n = 0
+
+    def _check(self, rc):
+        if rc < 0:
+            raise MpmError(rc, self.lib.mpm_group_last_error(self.g).decode())
+        return rc
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.lib.mpm_group_destroy(self.g)
+            self.g = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def upload(self, particles):
+        p = np.ascontiguousarray(particles, np.float32)
+        assert p.ndim == 2 and p.shape[1] == self.words
+        self._check(self.lib.mpm_group_upload_particles(self.g, p.ctypes.data, p.shape[0]))
+        self.n = p.shape[0]
+
+    def substep(self, n_steps=1, dt=0.0):
+        self._check(self.lib.mpm_group_substep(self.g, dt, n_steps))
+
+    def read(self):
+        out = np.empty((self.n, self.words), np.float32)
+        self._check(self.lib.mpm_group_read_particles(self.g, out.ctypes.data, self.n))
+        return out
+
+    def poll_status(self):
+        return self.lib.mpm_group_poll_status(self.g)
+
+    def slabs(self):
+        out = []
+        for k in range(self.n_slabs):
+            d, lo, hi, cnt = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_longlong()
+            self._check(self.lib.mpm_group_slab(self.g, k, ctypes.byref(d), ctypes.byref(lo), ctypes.byref(hi),
+                                                ctypes.byref(cnt)))
+            out.append((d.value, lo.value, hi.value, cnt.value))
+        return out

@@ -1,17 +1,20 @@
 """x-slab domain decomposition over several B200s.
 
 The grid is cut into slabs of whole base-cell columns; rank r owns columns [lo_r, hi_r) and every
-particle whose base cell (cpp_validation/mls-mpm88-explained.cpp:55) lies in them.  One substep:
+particle whose base cell (cpp_validation/mls-mpm88-explained.cpp:55) lies in them.  Per substep ONE
+fixed-size message goes to each x-neighbour (include/mpm.h, mpm_slab_*): the partial sums of the two node
+columns the slabs share (contiguous memory because x is the major grid index, :47), the emigrant count and
+the emigrant records.  The receiving handle adds the sums (shared columns are then computed redundantly and
+bit-identically on both sides), appends the immigrants and adds their share of the next P2G.  Counts and
+extents stay on the device, so nothing here ever waits for the GPU:
 
-    P2G (owned particles)  ->  ghost-column SUM with both x-neighbours (2 node columns each way,
-    contiguous memory because x is the major grid index, :47)  ->  grid update (shared columns are
-    computed redundantly, bit-identically)  ->  G2P  ->  particle MIGRATION to the neighbours.
+    [slab_begin -> exchange]   then per substep:   slab_step -> exchange     ...   slab_settle
 
-The engine (libmpm.so, one handle per GPU) only exposes device buffers and the phase calls; the bytes
-are moved here: `DistExchange` = torch.distributed P2P (NCCL over NVLink / NVSwitch, or gloo on CPU
-tensors in the tests), `LocalExchange` = device-to-device copies between handles that live in one
-process (single-GPU emulation of N slabs, used by the GPU parity tests).  No collective is needed:
-the pattern is nearest-neighbour only.
+The engine (libmpm.so, one handle per GPU) only exposes the message buffers; the bytes are moved here:
+`DistExchange` = torch.distributed P2P (NCCL over NVLink / NVSwitch, or gloo on CPU tensors in the tests),
+one grouped send/recv per substep; `LocalExchange` = device-to-device copies between handles that live in
+one process (single-GPU emulation of N slabs, used by the GPU parity tests).  No collective is needed: the
+pattern is nearest-neighbour only.
 """
 import numpy as np
 
@@ -96,57 +99,45 @@ class SlabRank:
     def __init__(self, engine, rank, world, device):
         self.e, self.rank, self.world, self.device = engine, rank, world, device
         self.has_lo, self.has_hi = rank > 0, rank < world - 1
-        h = engine.halo()
-        nb = h.bytes
-        self.halo_send_lo = dev_tensor(h.send_lo, nb, device)
-        self.halo_send_hi = dev_tensor(h.send_hi, nb, device)
-        self.halo_recv_lo = dev_tensor(h.recv_lo, nb, device)
-        self.halo_recv_hi = dev_tensor(h.recv_hi, nb, device)
-        m = engine.migration()
-        self.rec_bytes = m.record_bytes
-        cap = m.recv_capacity * m.record_bytes
-        self.mig_send_lo = dev_tensor(m.send_lo, cap, device)
-        self.mig_send_hi = dev_tensor(m.send_hi, cap, device)
-        self.mig_recv_lo = dev_tensor(m.recv_lo, cap, device)
-        self.mig_recv_hi = dev_tensor(m.recv_hi, cap, device)
+        d = engine.slab()
+        self.bytes = d.bytes
+        self.send_lo = dev_tensor(d.send_lo, d.bytes, device)
+        self.send_hi = dev_tensor(d.send_hi, d.bytes, device)
+        self.recv_lo = dev_tensor(d.recv_lo, d.bytes, device)
+        self.recv_hi = dev_tensor(d.recv_hi, d.bytes, device)
 
 
 class LocalExchange:
-    """All slabs live in this process (any mix of devices): plain device-to-device copies."""
+    """All slabs live in this process (any mix of devices): plain device-to-device copies.
+    `stream`: a torch stream that every handle ALSO launches on (mpm_config.stream): the copies are then ordered on
+    it and nothing synchronises -- with MPM_FLAG_OVERLAP the interior kernels (side streams) really run concurrently
+    with the staging, the copies and the next substep's message consumption."""
 
-    def __init__(self, ranks):
-        self.ranks = ranks
+    def __init__(self, ranks, stream=None):
+        self.ranks, self.stream = ranks, stream
 
-    def halo(self):
+    def _copy(self):
         for a, b in zip(self.ranks[:-1], self.ranks[1:]):  # a = lower slab, b = upper slab
-            a.e.synchronize()
-            b.e.synchronize()
-            b.halo_recv_lo.copy_(a.halo_send_hi)
-            a.halo_recv_hi.copy_(b.halo_send_lo)
-        self._sync()
+            b.recv_lo.copy_(a.send_hi, non_blocking=True)
+            a.recv_hi.copy_(b.send_lo, non_blocking=True)
 
-    def migrate(self):
-        descs = [r.e.migration() for r in self.ranks]  # synchronises each handle
-        n_in = [[0, 0] for _ in self.ranks]
-        for k, (a, b) in enumerate(zip(self.ranks[:-1], self.ranks[1:])):
-            up, down = descs[k].n_send_hi, descs[k + 1].n_send_lo
-            if up:
-                b.mig_recv_lo[:up * a.rec_bytes].copy_(a.mig_send_hi[:up * a.rec_bytes])
-            if down:
-                a.mig_recv_hi[:down * a.rec_bytes].copy_(b.mig_send_lo[:down * a.rec_bytes])
-            n_in[k + 1][0] = up
-            n_in[k][1] = down
-        self._sync()
-        return n_in
-
-    def _sync(self):
+    def exchange(self):
         import torch
+        if self.stream is not None:
+            with torch.cuda.stream(self.stream):
+                self._copy()
+            return
+        for r in self.ranks:
+            r.e.synchronize()  # the messages were staged on each handle's own stream
+        self._copy()
         for d in {r.device for r in self.ranks}:
-            torch.cuda.synchronize(d)
+            if d != "cpu":
+                torch.cuda.synchronize(d)
 
 
 class DistExchange:
-    """One slab per process: torch.distributed point-to-point with the two x-neighbours."""
+    """One slab per process: torch.distributed point-to-point with the two x-neighbours, one grouped
+    send/recv per substep, fixed sizes, no host synchronisation when the engine shares torch's stream."""
 
     def __init__(self, rank_obj, group=None, shared_stream=False):
         """shared_stream: the engine launches on torch's CURRENT stream (mpm_config.stream), so the
@@ -154,101 +145,72 @@ class DistExchange:
         import torch.distributed as dist
         self.r, self.dist, self.group, self.shared = rank_obj, dist, group, shared_stream
 
-    def _run(self, ops):
-        if ops:
-            for w in self.dist.batch_isend_irecv(ops):
-                w.wait()
-
-    def halo(self):
+    def exchange(self):
         r, d = self.r, self.dist
         if not self.shared:
-            r.e.synchronize()  # P2G wrote the send columns on the engine's own stream
+            r.e.synchronize()  # the messages were staged on the engine's own stream
         ops = []
         if r.has_hi:
-            ops += [d.P2POp(d.isend, r.halo_send_hi, r.rank + 1, self.group),
-                    d.P2POp(d.irecv, r.halo_recv_hi, r.rank + 1, self.group)]
+            ops += [d.P2POp(d.isend, r.send_hi, r.rank + 1, self.group),
+                    d.P2POp(d.irecv, r.recv_hi, r.rank + 1, self.group)]
         if r.has_lo:
-            ops += [d.P2POp(d.isend, r.halo_send_lo, r.rank - 1, self.group),
-                    d.P2POp(d.irecv, r.halo_recv_lo, r.rank - 1, self.group)]
-        self._run(ops)
-        self._sync()
-
-    def migrate(self):
-        import torch
-        r, d = self.r, self.dist
-        m = r.e.migration()  # synchronises; counts of the emigrants packed by G2P
-        dev = r.device
-        cnt_out = torch.tensor([m.n_send_lo, m.n_send_hi], dtype=torch.int64, device=dev)
-        cnt_in = torch.zeros(2, dtype=torch.int64, device=dev)
-        ops = []
-        if r.has_lo:
-            ops += [d.P2POp(d.isend, cnt_out[0:1], r.rank - 1, self.group),
-                    d.P2POp(d.irecv, cnt_in[0:1], r.rank - 1, self.group)]
-        if r.has_hi:
-            ops += [d.P2POp(d.isend, cnt_out[1:2], r.rank + 1, self.group),
-                    d.P2POp(d.irecv, cnt_in[1:2], r.rank + 1, self.group)]
-        self._run(ops)
-        n_lo, n_hi = (int(v) for v in cnt_in.tolist())
-        ops = []
-        rb = r.rec_bytes
-        if r.has_lo:
-            if m.n_send_lo:
-                ops.append(d.P2POp(d.isend, r.mig_send_lo[:m.n_send_lo * rb], r.rank - 1, self.group))
-            if n_lo:
-                ops.append(d.P2POp(d.irecv, r.mig_recv_lo[:n_lo * rb], r.rank - 1, self.group))
-        if r.has_hi:
-            if m.n_send_hi:
-                ops.append(d.P2POp(d.isend, r.mig_send_hi[:m.n_send_hi * rb], r.rank + 1, self.group))
-            if n_hi:
-                ops.append(d.P2POp(d.irecv, r.mig_recv_hi[:n_hi * rb], r.rank + 1, self.group))
-        self._run(ops)
-        self._sync()
-        return n_lo, n_hi
-
-    def _sync(self):
-        import torch
-        if not self.shared and self.r.device != "cpu" and torch.cuda.is_available():
-            torch.cuda.synchronize()
+            ops += [d.P2POp(d.isend, r.send_lo, r.rank - 1, self.group),
+                    d.P2POp(d.irecv, r.recv_lo, r.rank - 1, self.group)]
+        if ops:
+            for w in d.batch_isend_irecv(ops):
+                w.wait()  # NCCL: orders the current stream behind the transfer, does not block the host
+        if not self.shared and r.device != "cpu":
+            import torch
+            if torch.cuda.is_available():
+                torch.cuda.synchronize()
 
 
-def step_local(ranks, exchange, n_steps=1, dt=0.0):
+def step_local(ranks, exchange, n_steps=1, dt=0.0, settle=True):
     """n_steps substeps of all slabs held by this process (LocalExchange)."""
+    staged = [r.e.slab_begin(dt) for r in ranks]
+    assert all(staged) or not any(staged), "slab handles out of step"
+    if any(staged):
+        exchange.exchange()
     for _ in range(n_steps):
         for r in ranks:
-            r.e.step_p2g(dt)
-        exchange.halo()
+            r.e.slab_step(dt)
+        exchange.exchange()
+    if settle:
         for r in ranks:
-            r.e.step_halo_add(r.has_lo, r.has_hi)
-            r.e.step_grid_g2p(dt)
-        n_in = exchange.migrate()
-        for r, (n_lo, n_hi) in zip(ranks, n_in):
-            r.e.step_immigrate(n_lo, n_hi)
+            r.e.slab_settle()
 
 
-def step_dist(rank_obj, exchange, n_steps=1, dt=0.0):
+def step_dist(rank_obj, exchange, n_steps=1, dt=0.0, settle=True):
     """n_steps substeps of this process's slab (DistExchange)."""
     r = rank_obj
+    if r.e.slab_begin(dt):
+        exchange.exchange()
     for _ in range(n_steps):
-        r.e.step_p2g(dt)
-        exchange.halo()
-        r.e.step_halo_add(r.has_lo, r.has_hi)
-        r.e.step_grid_g2p(dt)
-        n_lo, n_hi = exchange.migrate()
-        r.e.step_immigrate(n_lo, n_hi)
+        r.e.slab_step(dt)
+        exchange.exchange()
+    if settle:
+        r.e.slab_settle()
 
 
-def make_local_cluster(engine_cls, p, dim, n_grid, world, devices=None, margin=1.5, **engine_kw):
-    """N slab handles in this process + their particles uploaded; -> (ranks, exchange, slabs)."""
+def make_local_cluster(engine_cls, p, dim, n_grid, world, devices=None, margin=1.5, shared_stream=False, **engine_kw):
+    """N slab handles in this process + their particles uploaded; -> (ranks, exchange, slabs).
+    shared_stream (single device): all handles launch on one torch stream and the exchange never synchronises."""
     slabs = partition(n_grid, world, align=engine_kw.get("bin_edge") or (8 if dim == 2 else 4))
     parts = scatter_particles(p, n_grid, slabs)
     ranks = []
+    stream = None
+    if shared_stream:
+        import torch
+        assert not devices or len(set(devices)) == 1
+        stream = torch.cuda.Stream(device=devices[0] if devices else 0)
+        engine_kw = dict(engine_kw, stream=stream.cuda_stream)
     for r, ((lo, hi), (rec, ids)) in enumerate(zip(slabs, parts)):
         dev = devices[r] if devices else 0
         cap = int(max(len(rec) * margin, len(rec) + 8192))
         e = engine_cls(dim=dim, n_grid=n_grid, capacity=cap, slab=(lo, hi), device=dev, **engine_kw)
         e.upload_ids(rec, ids)
         ranks.append(SlabRank(e, r, world, "cuda:%d" % dev))
-    return ranks, LocalExchange(ranks), slabs
+    return ranks, LocalExchange(ranks, stream), slabs
 
 
 def collect_local(ranks, n_total, words):

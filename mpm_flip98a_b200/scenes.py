@@ -132,13 +132,32 @@ def slab_fill_2d_count(n_grid, per_side=3, x_range=(0.05, 0.95), y_range=(0.05, 
     return max(0, c1 - c0) * (r1 - r0) * per_side * per_side
 
 
-def collapse_3d(n_grid=256, per_side=2, seed=4, y_top=0.35, xz=(0.05, 0.95)):
-    """BASELINE config 5: a 3D slab x,z in [0.05,0.95], y in [0.05,y_top], three bands along x."""
-    rng = np.random.RandomState(seed)
-    x = _jittered_box((xz[0], 0.05, xz[0]), (xz[1], y_top, xz[1]), n_grid, per_side, rng, 3)
-    t = (x[:, 0] - xz[0]) / (xz[1] - xz[0])
-    mat = np.minimum((t * 3).astype(np.int32), 2)
-    return make_records(x, mat, 3)
+def collapse_3d(n_grid=256, per_side=2, seed=4, y_top=0.35, xz=(0.05, 0.95), columns=None, strip=16):
+    """BASELINE config 5: a 3D slab x,z in [0.05,0.95], y in [0.05,y_top], three bands along x.
+
+    `columns=(c_lo, c_hi)` generates only the cell columns (x) of one x-slab, strip by strip with one seeded
+    stream per strip of `strip` columns, so that any partition yields the same global scene (the default,
+    columns=None, draws the whole box from a single stream)."""
+    def records(x):
+        t = (x[:, 0] - xz[0]) / (xz[1] - xz[0])
+        return make_records(x, np.clip((t * 3).astype(np.int32), 0, 2), 3)
+
+    if columns is None:
+        rng = np.random.RandomState(seed)
+        return records(_jittered_box((xz[0], 0.05, xz[0]), (xz[1], y_top, xz[1]), n_grid, per_side, rng, 3))
+    c0 = max(int(np.ceil(xz[0] * n_grid - 1e-9)), columns[0])
+    c1 = min(int(np.floor(xz[1] * n_grid + 1e-9)), columns[1])
+    parts = []
+    for s0 in range((c0 // strip) * strip, c1, strip):
+        a, b = max(s0, c0), min(s0 + strip, c1)
+        if a >= b:
+            continue
+        rng = np.random.RandomState((seed * 1000003 + s0) % (2 ** 31))
+        full = _jittered_box((max(s0 / n_grid, xz[0]), 0.05, xz[0]), (min((s0 + strip) / n_grid, xz[1]), y_top, xz[1]),
+                             n_grid, per_side, rng, 3)
+        keep = (full[:, 0] >= np.float32(a / n_grid)) & (full[:, 0] < np.float32(b / n_grid))
+        parts.append(records(full[keep]))
+    return np.concatenate(parts) if parts else np.zeros((0, 26), np.float32)
 
 
 def commented_three_blocks(seed=5):

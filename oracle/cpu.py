@@ -156,6 +156,13 @@ class Oracle:
                              s.ctypes.data_as(ctypes.c_void_p), V.ctypes.data_as(ctypes.c_void_p))
         return U, s, V
 
+    def rotation3(self, m):
+        """rotation factor of the 3D stress (Newton polar iteration, SVD fallback): 9 floats, column-major"""
+        m = np.ascontiguousarray(m, np.float32)
+        R = np.zeros(9, np.float32)
+        self.lib.oracle_rotation3(m.ctypes.data_as(ctypes.c_void_p), R.ctypes.data_as(ctypes.c_void_p))
+        return R
+
     def svd3(self, m):
         m = np.ascontiguousarray(m, np.float32)
         U, V = np.zeros(9, np.float32), np.zeros(9, np.float32)

@@ -2,8 +2,9 @@
 
 TEST INFRASTRUCTURE ONLY.  These parts have no counterpart in the reference ("parity
 unpinned"), so the fixture does not pin them to the reference -- it pins them to THEMSELVES: any later edit of
-oracle/mpm_oracle.cpp that changes their arithmetic (as the 3D Jacobi convergence rule did) has to regenerate this
-file on purpose.  Run:  make -C oracle && python oracle/make_extension_golden.py
+oracle/mpm_oracle.cpp that changes their arithmetic (as the 3D Jacobi convergence rule did in round 1, and the
+Newton-polar rotation of the 3D stress in round 2: 120 substeps of the 3D cases moved by 2e-7 relative in x and 6e-5 in v) has to
+regenerate this file on purpose.  Run:  make -C oracle && python oracle/make_extension_golden.py
 """
 import os
 import sys
@@ -41,6 +42,7 @@ def run():
     ms = (np.eye(3).reshape(1, 9) + 0.2 * rs.randn(64, 9)).astype(np.float32)
     out["svd3_in"] = ms
     out["svd3_out"] = np.stack([np.concatenate(O.svd3(m)) for m in ms])
+    out["rotation3_out"] = np.stack([O.rotation3(m) for m in ms])
     return out
 
 

@@ -556,6 +556,42 @@ inline void svd3(const M3 &A_in, M3 &U, float sig[3], M3 &V) {
   sig[2] = s[2];
 }
 
+// Rotation factor of the 3D stress: Newton's iteration for the polar decomposition, X <- (X + X^-T)/2 from X0 = F,
+// stopped when an iteration moves no entry by more than 2e-4 (the next iterate is then within fp32 rounding of R);
+// near-singular or inverted F takes U V^T of the Jacobi SVD above.  (Round 2: this replaced the SVD's U V^T in the
+// stress -- 20x cheaper on the GPU; both are this builder's definitions, the reference has no 3D code, and they
+// agree to ~1e-6.  The SVD still defines the plastic clamp.)
+inline M3 rotation3(const M3 &F) {
+  M3 X = F;
+  float scale = 0.0f;
+  for (int c = 0; c < 3; c++)
+    for (int k = 0; k < 3; k++) scale = std::fmax(scale, std::fabs(F.d[c][k]));
+  for (int it = 0; it < 12; it++) {
+    const float *a = X.d[0], *b = X.d[1], *c = X.d[2];
+    M3 K;
+    K.d[0][0] = b[1] * c[2] - b[2] * c[1]; K.d[0][1] = b[2] * c[0] - b[0] * c[2]; K.d[0][2] = b[0] * c[1] - b[1] * c[0];
+    K.d[1][0] = c[1] * a[2] - c[2] * a[1]; K.d[1][1] = c[2] * a[0] - c[0] * a[2]; K.d[1][2] = c[0] * a[1] - c[1] * a[0];
+    K.d[2][0] = a[1] * b[2] - a[2] * b[1]; K.d[2][1] = a[2] * b[0] - a[0] * b[2]; K.d[2][2] = a[0] * b[1] - a[1] * b[0];
+    const float det = a[0] * K.d[0][0] + a[1] * K.d[0][1] + a[2] * K.d[0][2];
+    if (!(det > 1e-6f * scale * scale * scale)) {
+      M3 U, V;
+      float sg[3];
+      svd3(F, U, sg, V);
+      return m3_mul(U, m3_transposed(V));
+    }
+    const float h = 0.5f / det;
+    float delta = 0.0f;
+    for (int cc = 0; cc < 3; cc++)
+      for (int k = 0; k < 3; k++) {
+        const float y = std::fma(h, K.d[cc][k], 0.5f * X.d[cc][k]);
+        delta = std::fmax(delta, std::fabs(y - X.d[cc][k]));
+        X.d[cc][k] = y;
+      }
+    if (delta <= 2e-4f) break;
+  }
+  return X;
+}
+
 void advance3(const OracleParams &P, float dt, P3 *particles, long long n, float *grid /*(n+1)^3*4*/,
               float *grid_post_p2g, float *vold /*(n+1)^3*3*/, int n_threads = 1) {
   const int num_grid = P.n_grid;
@@ -608,10 +644,7 @@ void advance3(const OracleParams &P, float dt, P3 *particles, long long n, float
     if (mat.kind == KIND_FLUID) {
       PF = m3_diag(lambda * (J - 1) * J);
     } else {
-      M3 U, V;
-      float sg[3];
-      svd3(p.F, U, sg, V);
-      M3 r = m3_mul(U, m3_transposed(V));
+      M3 r = rotation3(p.F);
       PF = m3_add(m3_mul(m3_scale(2 * mu, m3_sub(p.F, r)), m3_transposed(p.F)), m3_diag(lambda * (J - 1) * J));
     }
     M3 stress = m3_scale(-(dt * vol_p), m3_scale(Dinv, PF));
@@ -795,6 +828,12 @@ void oracle_svd2(const float *m, float *U, float *sig, float *V) {
   std::memcpy(U, &u, 16);
   std::memcpy(sig, &sg, 16);
   std::memcpy(V, &v, 16);
+}
+void oracle_rotation3(const float *m, float *R) {
+  M3 M, r;
+  std::memcpy(&M, m, 36);
+  r = rotation3(M);
+  std::memcpy(R, &r, 36);
 }
 void oracle_svd3(const float *m, float *U, float *sig3, float *V) {
   M3 M, u = m3_zero(), v = m3_zero();

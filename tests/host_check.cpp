@@ -263,7 +263,7 @@ void hostcheck_polar2(const float *m, float *R, float *S) {
 void hostcheck_rotation3(const float *m, float *R_svd, float *R_newton) {
   Mat<3> M;
   std::memcpy(&M, m, 36);
-  Mat<3> a = rotation_of(M), b = rotation_of_fast(M);
+  Mat<3> a = rotation_of_svd(M), b = rotation_of(M);
   std::memcpy(R_svd, &a, 36);
   std::memcpy(R_newton, &b, 36);
 }

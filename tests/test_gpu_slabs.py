@@ -14,9 +14,10 @@ from tests.util import bits, fields, rel_l2
 pytestmark = pytest.mark.gpu
 
 
-def run_slabs(p, dim, n_grid, world, steps, dt, vol_p, alpha=0.0, flags=0, rebin_every=0):
+def run_slabs(p, dim, n_grid, world, steps, dt, vol_p, alpha=0.0, flags=0, rebin_every=0, shared_stream=False):
     ranks, ex, slabs = parallel.make_local_cluster(mpm.Engine, p, dim, n_grid, world, dt=dt, vol_p=vol_p,
-                                                   alpha=alpha, flags=flags, rebin_every=rebin_every)
+                                                   alpha=alpha, flags=flags, rebin_every=rebin_every,
+                                                   shared_stream=shared_stream)
     parallel.step_local(ranks, ex, steps)
     out = parallel.collect_local(ranks, len(p), p.shape[1])
     status = [r.e.poll_status() for r in ranks]
@@ -96,6 +97,13 @@ def test_overlapped_schedule_wide_slabs(oracle, world):
     oracle.advance(P, dt, want, 1)
     got, status, counts, slabs = run_slabs(warm, 2, n, world, 1, dt, vol, flags=FLAG_OVERLAP)
     assert status == [0] * world and sum(counts) == len(p)
+    # the same on ONE shared stream without any host synchronisation: the interior kernels (side streams) overlap
+    # the staging, the copies and the consumption of the messages
+    got2, status2, counts2, _ = run_slabs(warm, 2, n, world, 3, dt, vol, flags=FLAG_OVERLAP, shared_stream=True)
+    got3, status3, counts3, _ = run_slabs(warm, 2, n, world, 3, dt, vol, flags=0)
+    assert status2 == [0] * world and sum(counts2) == len(p) and status3 == [0] * world
+    for k, v in fields(got3, 2).items():
+        assert rel_l2(fields(got2, 2)[k], v) <= 4e-5, (k, rel_l2(fields(got2, 2)[k], v))
     fw, fg = fields(want, 2), fields(got, 2)
     for k in fw:
         assert rel_l2(fg[k], fw[k]) <= 2e-5, (k, rel_l2(fg[k], fw[k]))  # C at 512^2: the reference's own reorder noise is 1e-5
@@ -105,8 +113,41 @@ def test_overlapped_schedule_wide_slabs(oracle, world):
         e.upload(warm)
         e.substep(steps)
         single = e.read()
-    got, status, counts, slabs = run_slabs(warm, 2, n, world, steps, dt, vol, flags=FLAG_OVERLAP, rebin_every=16)
+    got, status, counts, slabs = run_slabs(warm, 2, n, world, steps, dt, vol, flags=FLAG_OVERLAP, rebin_every=16,
+                                           shared_stream=True)
     assert status == [0] * world and sum(counts) == len(p)
     assert (parallel.owner_of(warm[:, 0], n, slabs) != parallel.owner_of(got[:, 0], n, slabs)).sum() > 100
     b0, b1 = scenes.bulk(single, 2), scenes.bulk(got, 2)
     assert np.abs(b0["com"] - b1["com"]).max() <= 1e-4 and abs(b0["ke"] - b1["ke"]) <= 1e-3 * b0["ke"]
+
+
+@pytest.mark.parametrize("n_slabs", [1, 2, 3])
+def test_group_handle_drives_slabs_from_the_c_abi(oracle, shipped, n_slabs):
+    """mpm_group_*: several slabs behind ONE handle (the calls a C++ main() makes): upload, substep, read in upload
+    order -- here all slabs on cuda:0 (a device may appear more than once); against the oracle and the migration
+    bookkeeping (every particle accounted for, slab particle counts change)."""
+    p = shipped["step1000"]
+    want = p.copy()
+    oracle.advance(make_params(), 1e-4, want, 1)
+    with mpm.Group([0] * n_slabs, dim=2, n_grid=80, capacity=len(p)) as g:
+        g.upload(p)
+        before = g.slabs()
+        assert sum(s[3] for s in before) == len(p) and before[0][1] == 0 and before[-1][2] == 80
+        g.substep(1)
+        got = g.read()
+        assert g.poll_status() == 0
+        fw, fg = fields(want, 2), fields(got, 2)
+        for k in fw:
+            assert rel_l2(fg[k], fw[k]) <= 1e-5, (k, rel_l2(fg[k], fw[k]))
+        g.substep(150)
+        later = g.read()
+        assert g.poll_status() == 0
+        after = g.slabs()
+    assert sum(s[3] for s in after) == len(p)
+    assert np.isfinite(later).all() and np.array_equal(bits(later[:, -1]), bits(p[:, -1]))
+    if n_slabs > 1:
+        assert [s[3] for s in after] != [s[3] for s in before], "the scene must migrate particles between the slabs"
+    ref = p.copy()
+    oracle.advance(make_params(), 1e-4, ref, 151)
+    b0, b1 = scenes.bulk(ref, 2), scenes.bulk(later, 2)
+    assert np.abs(b0["com"] - b1["com"]).max() <= 2e-3 * np.abs(b0["com"]).max()  # chaotic scene: reorder noise

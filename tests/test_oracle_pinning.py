@@ -141,3 +141,23 @@ def test_oracle_extensions_are_frozen(oracle):
         assert np.array_equal(bits(p), bits(gold[name])), name
     got = np.stack([np.concatenate(oracle.svd3(m)) for m in gold["svd3_in"]])
     assert np.array_equal(bits(got), bits(gold["svd3_out"]))
+    got = np.stack([oracle.rotation3(m) for m in gold["svd3_in"]])
+    assert np.array_equal(bits(got), bits(gold["rotation3_out"]))
+
+
+def test_rotation3_properties(oracle):
+    """The oracle's 3D rotation factor (Newton polar iteration; no counterpart in the reference) against the spec of
+    the reference's own -- dead -- decomposition test (taichi.h:8431-8445: m = R S, R R^T = I, det R = 1, S = S^T,
+    tolerance 3e-5) and against U V^T of the oracle's Jacobi SVD."""
+    rs = np.random.RandomState(5)
+    for k in range(2000):
+        m = (np.eye(3) + (0.05 if k % 2 else 0.4) * rs.randn(3, 3)).astype(np.float32)
+        if np.linalg.det(m.astype(np.float64)) < 0.05:
+            continue
+        R = oracle.rotation3(m.T.reshape(-1)).reshape(3, 3).T.astype(np.float64)   # column-major storage
+        S = R.T @ m.astype(np.float64)
+        assert np.abs(R @ R.T - np.eye(3)).max() < 3e-5 and abs(np.linalg.det(R) - 1) < 3e-5
+        assert np.abs(S - S.T).max() < 3e-5 * max(1.0, np.abs(S).max())
+        U, s, V = oracle.svd3(m.T.reshape(-1))
+        Rs = U.reshape(3, 3).T.astype(np.float64) @ V.reshape(3, 3).T.astype(np.float64).T
+        assert np.abs(R - Rs).max() < 3e-6

@@ -1,7 +1,8 @@
 """N > 1 host logic on CPU (no GPU): slab partition / ownership, and the exchange protocol of
 mpm_flip98a_b200.parallel run for real over torch.distributed `gloo`, world_size 2, with a numpy
 stand-in for the engine (tests/fake_slab_engine.py).  Checked against the same stand-in on one slab:
-identical ghost-summed grids, no particle lost or duplicated, ids preserved."""
+identical ghost-summed grids in every substep (although a migrating particle's P2G share is split between sender
+and receiver), no particle lost or duplicated, ids preserved."""
 import os
 import subprocess
 import sys
@@ -54,15 +55,9 @@ e = FakeEngine(n, slabs[rank])
 e.upload_ids(rec, ids)
 r = parallel.SlabRank(e, rank, world, "cpu")
 ex = parallel.DistExchange(r)
-grids = []
-for s in range(40):
-    e.step_p2g()
-    ex.halo()
-    e.step_halo_add(r.has_lo, r.has_hi)
-    grids.append(e.grid.copy())
-    e.step_grid_g2p()
-    n_lo, n_hi = ex.migrate()
-    e.step_immigrate(n_lo, n_hi)
+parallel.step_dist(r, ex, 25)
+parallel.step_dist(r, ex, 15)   # a second call continues from the settled state without a begin-exchange
+grids = e.complete_grids
 rec, ids = e.read_ids()
 np.savez(sys.argv[3] + ".%d.npz" % rank, rec=rec, ids=ids, grid=np.stack(grids), lo=slabs[rank][0])
 dist.destroy_process_group()
@@ -84,12 +79,11 @@ def test_two_rank_gloo_exchange(tmp_path):
     # single-slab run of the same stand-in
     e = FakeEngine(80, (0, 80))
     e.upload_ids(p, np.arange(len(p), dtype=np.int32))
-    grids = []
-    for s in range(40):
-        e.step_p2g()
-        grids.append(e.grid.copy())
-        e.step_grid_g2p()
-        e.step_immigrate(0, 0)
+    assert not e.slab_begin()
+    for s_ in range(40):
+        e.slab_step()
+    e.slab_settle()
+    grids = e.complete_grids
     grids = np.stack(grids)
     moved = 0
     for o in outs:

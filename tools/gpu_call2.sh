@@ -10,7 +10,7 @@ MPM_SKIP_HUGE=1 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test
 # ncu: launch list, then the full capture of the substep kernel (same command exited 0 directly before)
 CMD="python bench.py --steps 4 --warmup 3 --warm-substeps 300 --no-cpu --e2e-calls 1"
 $CMD > gpurun_out/r2b_plain.log 2>&1 && \
-ncu --metrics gpu__time_duration.sum --clock-control none -s 2400 -c 120 --csv --log-file gpurun_out/r2b_launches_c4.csv $CMD > gpurun_out/r2b_ncu_launch.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 600 -c 160 --csv --log-file gpurun_out/r2b_launches_c4.csv $CMD > gpurun_out/r2b_ncu_launch.log 2>&1
 echo "ncu launches rc=$?" >> gpurun_out/r2b_box.txt
 $CMD > gpurun_out/r2b_plain2.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"k_substep2d|k_grid_update|k_count_rank" -s 640 -c 6 -o gpurun_out/r2b_prof_c4 $CMD > gpurun_out/r2b_ncu_full.log 2>&1
