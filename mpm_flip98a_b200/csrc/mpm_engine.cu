@@ -93,6 +93,10 @@ struct mpm_handle {
   // while it writes the NEW one (bs = index of the set that describes the current storage)
   int *bin_start_buf[2] = {nullptr, nullptr};
   int *active_bins_buf[2] = {nullptr, nullptr};  // compacted ids of the non-empty bins
+  int4 *chunks_buf[2] = {nullptr, nullptr};      // work list of the 2D substep kernel (see launch_active_chunks)
+  unsigned *chunk_offs = nullptr;                // its scan scratch, n_bins + 4
+  long long chunks_cap = 0;
+  int n_chunks = 0, chunk_lo_end = 0, chunk_hi_begin = 0;  // overlap: boundary-lo | interior | boundary-hi chunks
   int bs = 0;
   int *bin_start = nullptr;         // == bin_start_buf[bs]
   unsigned *active_offs = nullptr;  // scan scratch, n_bins + 2
@@ -355,7 +359,7 @@ int mpm_handle::init() {
     if ((rc = dalloc(&bin_start_buf[b], (size_t)G.n_bins + 4)) || (rc = dalloc(&active_bins_buf[b], (size_t)G.n_bins + 1)))
       return rc;
   bin_start = bin_start_buf[0];
-  MPM_CUDA(cudaHostAlloc((void **)&resort_host, 32, cudaHostAllocDefault));
+  MPM_CUDA(cudaHostAlloc((void **)&resort_host, 64, cudaHostAllocDefault));
   MPM_CUDA(cudaEventCreateWithFlags(&resort_ev, cudaEventDisableTiming));
   if (multi) {
     // K = records per message: far above what one substep moves across a cut (a column of cells times the CFL
@@ -387,6 +391,13 @@ int mpm_handle::init() {
   pipelined = fused || multi;
   if (pipelined)
     if ((rc = dalloc(&grid_next, (size_t)nodes))) return rc;
+  if (fast2d()) {
+    // one entry per chunk: at most one per non-empty bin plus one per full chunk of particles
+    chunks_cap = (long long)G.n_bins + cap / substep2d_chunk_capacity() + 2;
+    for (int b = 0; b < 2; b++)
+      if ((rc = dalloc(&chunks_buf[b], (size_t)chunks_cap))) return rc;
+    if ((rc = dalloc(&chunk_offs, (size_t)G.n_bins + 4))) return rc;
+  }
   overlap = fused && multi && (cfg.flags & MPM_FLAG_OVERLAP);
   if (overlap) {
     {
@@ -499,6 +510,10 @@ int mpm_handle::begin_resort() {
   launch_active_bins(ns, G.n_bins, active_offs, sb.scan_tmp, na, stream);
   MPM_CUDA(cudaMemcpyAsync(&resort_host[0], active_offs + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
   MPM_CUDA(cudaMemcpyAsync(&resort_host[1], ns + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
+  if (chunk_offs) {
+    launch_active_chunks(ns, G.n_bins, G.nb[1], substep2d_chunk_capacity(), chunk_offs, sb.scan_tmp, chunks_buf[bs ^ 1], stream);
+    MPM_CUDA(cudaMemcpyAsync(&resort_host[4], chunk_offs + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
+  }
   if (overlap) {
     // the active list is sorted by bin id (x-major): boundary-lo bins are a prefix, boundary-hi bins a suffix;
     // the scan scratch holds "active bins with a smaller id" for every bin
@@ -507,6 +522,10 @@ int mpm_handle::begin_resort() {
     const int hi_bin = cfg.slab_hi < cfg.n_grid ? (G.nb[0] - 2 > 0 ? G.nb[0] - 2 : 0) * col : G.n_bins;
     MPM_CUDA(cudaMemcpyAsync(&resort_host[2], active_offs + lo_bin, 4, cudaMemcpyDeviceToHost, stream));
     MPM_CUDA(cudaMemcpyAsync(&resort_host[3], active_offs + hi_bin, 4, cudaMemcpyDeviceToHost, stream));
+    if (chunk_offs) {
+      MPM_CUDA(cudaMemcpyAsync(&resort_host[5], chunk_offs + lo_bin, 4, cudaMemcpyDeviceToHost, stream));
+      MPM_CUDA(cudaMemcpyAsync(&resort_host[6], chunk_offs + hi_bin, 4, cudaMemcpyDeviceToHost, stream));
+    }
   }
   MPM_CUDA(cudaEventRecord(resort_ev, stream));
   resort_pending = true;
@@ -530,6 +549,15 @@ int mpm_handle::end_resort() {
   if (overlap) {
     act_lo_end = resort_host[2];
     act_hi_begin = resort_host[3] > act_lo_end ? resort_host[3] : act_lo_end;
+  }
+  if (chunk_offs) {
+    n_chunks = resort_host[4];
+    chunk_lo_end = 0;
+    chunk_hi_begin = n_chunks;
+    if (overlap) {
+      chunk_lo_end = resort_host[5];
+      chunk_hi_begin = resort_host[6] > chunk_lo_end ? resort_host[6] : chunk_lo_end;
+    }
   }
   return MPM_OK;
 }
@@ -580,6 +608,7 @@ int mpm_handle::rebin_storage() {
     n_binned = 0;
     G.n_active = 0;
     act_lo_end = act_hi_begin = 0;
+    n_chunks = chunk_lo_end = chunk_hi_begin = 0;
     return MPM_OK;
   }
   if (!fused_resort_now) {
@@ -704,7 +733,8 @@ int mpm_handle::step_grid_g2p(float dt) {
       sa.dt_p2g = dt;
       sa.s = s2[cur];
       sa.d = s2[cur ^ 1];
-      sa.bin_start = bin_start;
+      sa.chunks = chunks_buf[bs];
+      sa.n_chunks = n_chunks;
       sa.new_start = bin_start_buf[bs ^ 1];
       sa.key = sb.key[0];
       sa.rank = (const unsigned *)sb.val[0];
@@ -716,11 +746,16 @@ int mpm_handle::step_grid_g2p(float dt) {
       sa.mig = mig;
     }
     const bool flip = P.alpha != 0.0f;
-    auto run_bins = [&](const BinGeom &Gx, MigPtrs mg, cudaStream_t st) {
+    // part: 0 = everything, 1 = boundary-lo, 2 = interior, 3 = boundary-hi (overlapped schedule)
+    auto run_bins = [&](const BinGeom &Gx, MigPtrs mg, cudaStream_t st, int part) {
       if (fast) {
         Substep2dArgs x = sa;
         x.G = Gx;
         x.mig = mg;
+        const int c0 = part == 0 || part == 1 ? 0 : (part == 2 ? chunk_lo_end : chunk_hi_begin);
+        const int c1 = part == 0 || part == 3 ? n_chunks : (part == 1 ? chunk_lo_end : chunk_hi_begin);
+        x.chunks = sa.chunks + c0;
+        x.n_chunks = c1 - c0;
         launch_substep2d(x, flip, mg.enabled != 0, resort, st);
       } else if (D == 2) {
         launch_g2p2g<2>(P, Gx, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mg, strict, st);
@@ -756,10 +791,10 @@ int mpm_handle::step_grid_g2p(float dt) {
         Phase ph(this, MPM_PHASE_MIGRATE, 2);  // accounted with the migration work they feed
         BinGeom Gb = G;
         Gb.n_active = act_lo_end;
-        if (Gb.n_active > 0) run_bins(Gb, mig, stream);
+        if (Gb.n_active > 0) run_bins(Gb, mig, stream, 1);
         Gb.active = G.active + act_hi_begin;
         Gb.n_active = G.n_active - act_hi_begin;
-        if (Gb.n_active > 0) run_bins(Gb, mig, stream);
+        if (Gb.n_active > 0) run_bins(Gb, mig, stream, 3);
         run_tail();
       }
       // interior bins on the side stream: run while the caller exchanges the boundary
@@ -771,13 +806,13 @@ int mpm_handle::step_grid_g2p(float dt) {
         Gi.n_active = act_hi_begin - act_lo_end;
         MigPtrs mi = mig;
         mi.interior = 1;
-        run_bins(Gi, mi, side);
+        run_bins(Gi, mi, side, 2);
       }
       MPM_CUDA(cudaEventRecord(ev_side_done, side));
       side_busy = true;
     } else {
       Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
-      if (n_binned > 0) run_bins(G, mig, stream);
+      if (n_binned > 0) run_bins(G, mig, stream, 0);
       run_tail();
     }
     if (resort) {

@@ -65,7 +65,8 @@ struct Substep2dArgs {
   float dt_g2p, dt_p2g;
   SoA<2> s;                   // particle storage (updated in place unless RESORT)
   SoA<2> d;                   // RESORT: the other storage buffer
-  const int *bin_start;       // bin ranges of `s`
+  const int4 *chunks;         // work list: (bin, first slot, particles, bin x << 16 | bin y), one CTA each
+  int n_chunks;
   const int *new_start;       // RESORT: bin starts of the new order
   const unsigned *key;        // RESORT: new bin of slot i (k_count_rank, positions before this substep)
   const unsigned *rank;       // RESORT: rank of slot i inside its new bin
@@ -77,6 +78,7 @@ struct Substep2dArgs {
   MigPtrs mig;
 };
 void launch_substep2d(const Substep2dArgs &a, bool flip, bool mig, bool resort, cudaStream_t st);
+int substep2d_chunk_capacity();  // particles per work-list entry (the kernel's shared-memory chunk)
 
 // ---- AoS <-> SoA at the C-ABI ------------------------------------------------------------------
 // records [first, first+count) of the caller's AoS -> SoA slots [first, first+count), id = index
@@ -122,6 +124,10 @@ void launch_bin_starts(const unsigned *sorted_key, long long n, int n_bins, int 
 void launch_iota(int *v, long long n, cudaStream_t st);
 // active[0..count) = ids of the non-empty bins, ascending; offs = scratch of n_bins+1 u32; count is written to offs[n_bins]
 void launch_active_bins(const int *bin_start, int n_bins, unsigned *offs, unsigned *scan_tmp, int *active, cudaStream_t st);
+// chunks[0..count) = (bin, first slot, particles, bin x << 16 | bin y) per chunk of <= cap particles of a non-empty
+// bin, ascending bin; offs = scratch of n_bins+1 u32 (afterwards: chunks before bin b); count -> offs[n_bins]
+void launch_active_chunks(const int *bin_start, int n_bins, int nb_y, int cap, unsigned *offs, unsigned *scan_tmp,
+                          int4 *chunks, cudaStream_t st);
 // exclusive scan of unsigned data[n] in place (tmp: scan_tmp_elems(n))
 void exclusive_scan_u32(unsigned *data, long long n, unsigned *tmp, cudaStream_t st);
 

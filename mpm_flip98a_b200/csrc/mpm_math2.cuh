@@ -4,12 +4,16 @@
 // the columns of C and F (column-major like taichi.h:7575), the per-axis B-spline weights.
 //
 // Exactness: mul2 / add2 / sub2 are IEEE round-to-nearest per component, so a packed expression that keeps
-// the reference's association is BITWISE the scalar one.  stencil2(), affine2() and g2p_finish2() keep it
-// (same statements as make_stencil / p2g_affine / g2p_finish, cpp_validation/mls-mpm88-explained.cpp
+// the reference's association is, as written, BITWISE the scalar one.  stencil2(), affine2() and g2p_finish2()
+// keep it (same statements as make_stencil / p2g_affine / g2p_finish, cpp_validation/mls-mpm88-explained.cpp
 // :55-64, :67-89, :159-178) and are checked bitwise against the oracle on the host
-// (tests/test_host_math.py::test_packed2d_*).  gather2() is the fast separable form of :147-156
-// (fused multiply-adds, algebraically identical, ~1e-7 relative from the reference association);
-// MPM_FLAG_STRICT never reaches this header.
+// (tests/test_host_math.py::test_packed2d_*).  ON THE DEVICE there is one licence: ptxas (CUDA 12.9) contracts a
+// mul.rn.f32x2 feeding an add.rn.f32x2 into a single FFMA2 -- -fmad=false does not reach the packed type -- so a
+// packed multiply-add may round once instead of twice (<= 1 ulp, the size of the reference's own summation-order
+// noise).  The integer base cell is therefore formed with scalar mul.rn / sub.rn and stays bit-exact.
+// gather2() is the fast separable form of :147-156 (fused multiply-adds by design, algebraically identical, ~1e-7
+// relative from the reference association).  MPM_FLAG_STRICT never reaches this header: the scalar kernels are
+// bit-faithful.
 #pragma once
 #include "mpm_math.cuh"
 
@@ -68,11 +72,12 @@ struct Sten2 {
 };
 MPM_HD Sten2 stencil2(f2 x, float inv_dx) {
   Sten2 s;
-  const f2 t = mul2(x, sp2(inv_dx));     // x*inv_dx, rounded before the subtraction (:55, :57)
-  const f2 tb = add2(t, sp2(-0.5f));
-  s.bx = (int)tb.x;                      // truncation, taichi.h:7185
-  s.by = (int)tb.y;
-  s.fx = sub2(t, mk2((float)s.bx, (float)s.by));
+  // scalar on purpose: the integer cell must be bit-exact, and ptxas (CUDA 12.9) contracts a packed
+  // mul.rn.f32x2 + add.rn.f32x2 pair into one FFMA2 whatever -fmad says; mul.rn.f32 / sub.rn.f32 it never touches
+  const float tx = MPM_MUL_RN(x.x, inv_dx), ty = MPM_MUL_RN(x.y, inv_dx);  // rounded before the subtraction (:55, :57)
+  s.bx = (int)MPM_SUB_RN(tx, 0.5f);      // truncation, taichi.h:7185
+  s.by = (int)MPM_SUB_RN(ty, 0.5f);
+  s.fx = mk2(MPM_SUB_RN(tx, (float)s.bx), MPM_SUB_RN(ty, (float)s.by));
   const f2 a = sub2(sp2(1.5f), s.fx), b = sub2(s.fx, sp2(1.0f)), c = sub2(s.fx, sp2(0.5f));
   s.w[0] = mul2(sp2(0.5f), mul2(a, a));         // :61
   s.w[1] = sub2(sp2(0.75f), mul2(b, b));        // :62

@@ -329,6 +329,31 @@ template void launch_reorder_scatter<2>(const SoA<2> &, const SoA<2> &, long lon
 template void launch_reorder_scatter<3>(const SoA<3> &, const SoA<3> &, long long, long long, int, const int *,
                                         const unsigned *, const unsigned *, cudaStream_t, const int *);
 
+// Work list of the 2D substep kernel: one entry per CHUNK of at most `cap` particles of a non-empty bin,
+// (bin, first slot, particles, bin x << 16 | bin y).  A CTA reads its entry with one load (no bin -> range -> particle chain of
+// dependent loads at CTA start), and a bin that a collapsing scene has filled far beyond the average is spread
+// over several CTAs instead of serialising its chunks in one.
+__global__ void k_flag_chunks(const int *__restrict__ bin_start, int n_bins, int cap, unsigned *__restrict__ offs) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= n_bins) offs[b] = b < n_bins ? (unsigned)((bin_start[b + 1] - bin_start[b] + cap - 1) / cap) : 0u;
+}
+__global__ void k_fill_chunks(const int *__restrict__ bin_start, int n_bins, int nb_y, int cap,
+                              const unsigned *__restrict__ offs, int4 *__restrict__ chunks) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_bins) return;
+  const int s0 = bin_start[b], cnt = bin_start[b + 1] - s0;
+  const int xy = ((b / nb_y) << 16) | (b % nb_y);  // 2D bin coordinates (the only user is the 2D substep kernel)
+  unsigned o = offs[b];
+  for (int c0 = 0; c0 < cnt; c0 += cap) chunks[o++] = make_int4(b, s0 + c0, min(cap, cnt - c0), xy);
+}
+void launch_active_chunks(const int *bin_start, int n_bins, int nb_y, int cap, unsigned *offs, unsigned *scan_tmp,
+                          int4 *chunks, cudaStream_t st) {
+  unsigned blocks = (unsigned)((n_bins + 1 + 255) / 256);
+  k_flag_chunks<<<blocks, 256, 0, st>>>(bin_start, n_bins, cap, offs);
+  exclusive_scan_u32(offs, (long long)n_bins + 1, scan_tmp, st);  // offs[n_bins] = number of chunks
+  k_fill_chunks<<<blocks, 256, 0, st>>>(bin_start, n_bins, nb_y, cap, offs, chunks);
+}
+
 __global__ void k_iota(int *v, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) v[i] = (int)i;

@@ -1,5 +1,6 @@
 // mpm_substep2d.cu -- the 2D substep kernel (default path, single GPU and x-slabs): G2P of substep n and
-// P2G of substep n+1 in one pass over the particles, one CTA per non-empty bin of 8x8 cells.
+// P2G of substep n+1 in one pass over the particles, one CTA per chunk (<= 768 particles) of a non-empty bin of
+// 8x8 cells.
 //
 // Reference statements (cpp_validation/mls-mpm88-explained.cpp): :134-179 (G2P: gather, advect, F update,
 // SVD clamp, Jp) of the current substep, then :53-102 (P2G) of the next one on the state still in registers.
@@ -13,7 +14,9 @@
 //   * 32-bit slab-local indices, one address computation per stencil row;
 //   * the per-chunk scans run on all four warps (packed count|items scan), item descriptors are built once
 //     per cell (no integer division per work item);
-//   * records split into two float4 planes (half the shared-memory bank conflicts of 32-byte records).
+//   * records split into two float4 planes (half the shared-memory bank conflicts of 32-byte records);
+//   * a work list entry per chunk, read with ONE load (the round-1 chain active bin -> bin range -> particles cost
+//     three dependent memory latencies at every CTA start), dense bins spread over several CTAs.
 // RESORT = true additionally performs the storage re-sort on the fly: each particle's new state is written
 // to its slot in the OTHER storage buffer (slot = new bin start + rank, both computed from the positions
 // before this substep by k_count_rank), so a re-sort costs one 12-byte pass instead of a radix sort plus a
@@ -25,7 +28,10 @@ namespace mpm {
 
 namespace {
 
-constexpr int B = 8, NT = 128, CAP = 768, M = 1, L = B + 2 * M, NC = L * L;
+#ifndef MPM_SUBSTEP2D_CAP
+#define MPM_SUBSTEP2D_CAP 768
+#endif
+constexpr int B = 8, NT = 128, CAP = MPM_SUBSTEP2D_CAP, M = 1, L = B + 2 * M, NC = L * L;
 constexpr int RM = 8;                       // a cell with more records is split evenly into ceil(n/RM) items
 constexpr int MAXI = NC + CAP / RM + 1;     // work items per chunk, upper bound
 
@@ -111,17 +117,15 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
   __shared__ int wtot[4], n_items_sh;
   const Params &P = A.P;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int bin = A.G.active ? A.G.active[blockIdx.x] : (int)blockIdx.x;
-  const int s0 = A.bin_start[bin], s1 = A.bin_start[bin + 1];
-  if (s0 >= s1) return;
-  const int ox = (bin / A.G.nb[1]) * B + P.slab_lo - M, oy = (bin % A.G.nb[1]) * B - M;  // global cell of local cell 0
+  const int4 work = A.chunks[blockIdx.x];  // one load: no bin -> range -> particle chain at CTA start
+  const int c0 = work.y, m = work.z;
+  const int ox = (work.w >> 16) * B + P.slab_lo - M, oy = (work.w & 0xffff) * B - M;  // global cell of local cell 0
   const int n1 = P.n1;
   const float s4 = 4 * P.inv_dx;
   const int x_lo = P.slab_lo, x_hi = min(P.slab_hi, P.n_grid - 1) - 1;  // clamp range of base x (clamp_base)
   unsigned n_fallback = 0;
   float vmax = 0.0f;  // fastest particle of this thread (max norm): feeds the re-sort interval (CFL), see engine
-  for (int c0 = s0; c0 < s1; c0 += CAP) {
-    const int m = min(CAP, s1 - c0);
+  {
     if (tid < NC) cnt[tid] = 0;
     __syncthreads();
     // ---------------- phase 1: thread per particle (G2P of this substep, P2G record of the next) -------------
@@ -304,7 +308,6 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
         atomicAdd(gp + a * n1 + 2, make_float4(acc[a][2].x, acc[a][2].y, m2[a], 0.0f));
       }
     }
-    if (c0 + CAP < s1) __syncthreads();  // another chunk follows: shared arrays are reused
   }
   if (A.stats) {
     if (n_fallback) {
@@ -319,8 +322,10 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
   }
 }
 
+int substep2d_chunk_capacity() { return CAP; }
+
 void launch_substep2d(const Substep2dArgs &a, bool flip, bool mig, bool resort, cudaStream_t st) {
-  const int grid = a.G.active ? a.G.n_active : a.G.n_bins;
+  const int grid = a.n_chunks;
   if (grid <= 0) return;
 #define MPM_S2D(F_, M_, R_) k_substep2d<F_, M_, R_><<<grid, NT, 0, st>>>(a)
   if (flip) {
