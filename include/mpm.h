@@ -60,6 +60,13 @@ enum {
   MPM_FLAG_OVERLAP = 1 << 5,          /* x-slab handles on the fused schedule: bins >= 2 bin columns away from the
                                          slab cuts run on a side stream while the boundary bins finish first, so
                                          the caller's migration / halo exchange overlaps the interior compute */
+  MPM_FLAG_DETERMINISTIC = 1 << 6,    /* fixed summation order: the storage is stably sorted by cell before every substep
+                                         and P2G runs one thread per grid node, adding the contributions of its 3^d
+                                         cells' particles sequentially in storage order -- the order the reference's
+                                         serial loop (:53-102) would use on that array.  Two runs are bit-identical and
+                                         the grid after P2G (total mass included) is BITWISE the CPU oracle's on the
+                                         same particle order.  Exact association throughout; whole-domain handles
+                                         only; a validation mode, ~10x slower. */
   MPM_FLAG_STRICT = 1 << 2            /* binned path: P2G node contributions (:92-100) and the G2P gather
                                          (:153-154) keep the reference's exact association instead of the
                                          separable / hoisted FMA forms (algebraically identical, ~1e-7
@@ -93,7 +100,9 @@ typedef struct mpm_config {
   int rebin_every;    /* re-sort the particle storage by bin every this many substeps; <0 = never;
                          0 = engine default: 32 on the naive path, adaptive 2..512 on the binned path
                          (0.75 cells / the largest per-substep displacement the kernels measure) */
-  int reserved[6];
+  int mig_records;    /* x-slab handles: emigrant records per message (must be the same on every handle of a
+                         decomposition); 0 = engine default, 2 x the nodes of a cut clamped to [4096, 262144] */
+  int reserved[5];
 } mpm_config;
 
 typedef struct mpm_handle mpm_handle;

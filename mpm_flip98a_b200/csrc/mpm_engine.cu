@@ -85,6 +85,12 @@ struct mpm_handle {
     return binned ? rebin_interval : 32;
   }
   bool binned = false;                      // CTA-per-bin P2G (default) vs MPM_FLAG_NAIVE
+  bool deterministic = false;               // MPM_FLAG_DETERMINISTIC (mpm_deterministic.cu)
+  float *det_rec = nullptr;
+  int *det_cell_start = nullptr;
+  long long det_cells = 0;
+  int det_key_bits = 0;
+  int det_sort_and_p2g(float dt);
 
   // binning
   BinGeom G;
@@ -99,6 +105,8 @@ struct mpm_handle {
   int n_chunks = 0, chunk_lo_end = 0, chunk_hi_begin = 0;  // overlap: boundary-lo | interior | boundary-hi chunks
   int bs = 0;
   int *bin_start = nullptr;         // == bin_start_buf[bs]
+  int *cell_start = nullptr;        // re-sort scratch: first slot of every cell (n_bins * cpb + 4), see begin_resort
+  long long n_cells() const { return (long long)G.n_bins * G.cpb; }
   unsigned *active_offs = nullptr;  // scan scratch, n_bins + 2
   int *cell_dev = nullptr;
   int key_bits = 0;
@@ -267,6 +275,8 @@ static int validate(const mpm_config &c, std::string &why) {
   if (c.slab_lo < 0 || c.slab_hi > c.n_grid || c.slab_lo >= c.slab_hi) BAD("bad slab [%d,%d)", c.slab_lo, c.slab_hi);
   if ((c.slab_lo > 0 || c.slab_hi < c.n_grid) && c.slab_hi - c.slab_lo < 2) BAD("a slab must own at least 2 columns [%d,%d)", c.slab_lo, c.slab_hi);
   if (c.bin_edge < 0 || c.bin_edge > 64) BAD("bin_edge must be 0..64 (got %d)", c.bin_edge);
+  if ((c.flags & MPM_FLAG_DETERMINISTIC) && (c.slab_lo > 0 || c.slab_hi < c.n_grid))
+    BAD("MPM_FLAG_DETERMINISTIC needs a whole-domain handle (an x-slab cut would split a node's sum)");
   return MPM_OK;
 #undef BAD
 }
@@ -352,22 +362,25 @@ int mpm_handle::init() {
   if ((rc = dalloc(&sb.hist, sort_hist_elems(cap)))) return rc;
   {  // the scan scratch serves the radix histograms and the active-bin compaction (n_bins + 1 flags)
     long long longest = (long long)sort_hist_elems(cap);
-    if ((long long)G.n_bins + 2 > longest) longest = (long long)G.n_bins + 2;
+    if (n_cells() + 4 > longest) longest = n_cells() + 4;
     if ((rc = dalloc(&sb.scan_tmp, scan_tmp_elems(longest)))) return rc;
   }
   for (int b = 0; b < 2; b++)
     if ((rc = dalloc(&bin_start_buf[b], (size_t)G.n_bins + 4)) || (rc = dalloc(&active_bins_buf[b], (size_t)G.n_bins + 1)))
       return rc;
   bin_start = bin_start_buf[0];
+  if ((rc = dalloc(&cell_start, (size_t)n_cells() + 4))) return rc;
   MPM_CUDA(cudaHostAlloc((void **)&resort_host, 64, cudaHostAllocDefault));
   MPM_CUDA(cudaEventCreateWithFlags(&resort_ev, cudaEventDisableTiming));
   if (multi) {
-    // K = records per message: far above what one substep moves across a cut (a column of cells times the CFL
-    // number), small enough that the fixed-size message stays a few MB
-    long long K = cap / 1024;
-    if (K < 16384) K = 16384;
-    if (K > (1 << 18)) K = 1 << 18;
-    if (K > cap / 4) K = cap / 4 > 64 ? cap / 4 : 64;  // small handles (tests)
+    // K = records per message.  Every handle of a decomposition must arrive at the same number (the messages have a
+    // fixed size), so it depends on the GLOBAL grid only: twice the nodes of a cut (a column / plane of cells at
+    // ~8-16 particles per cell times a CFL number <= 0.1-0.25), unless mpm_config.mig_records says otherwise
+    long long K = cfg.mig_records > 0 ? cfg.mig_records : halo_nodes();
+    if (cfg.mig_records <= 0) {
+      if (K < 4096) K = 4096;
+      if (K > (1 << 18)) K = 1 << 18;
+    }
     mig.cap = (int)K;
     mig.enabled = 1;
     msg_hdr = (size_t)halo_nodes() * sizeof(float4);
@@ -385,7 +398,17 @@ int mpm_handle::init() {
     MPM_CUDA(cudaMemsetAsync(dev_ext, 0, 16, stream));
   }
   if ((rc = dalloc(&active_offs, (size_t)G.n_bins + 4))) return rc;
-  binned = !(cfg.flags & MPM_FLAG_NAIVE) && (D == 2 ? p2g_cells_supported<2>(G) : p2g_cells_supported<3>(G));
+  deterministic = (cfg.flags & MPM_FLAG_DETERMINISTIC) != 0;
+  binned = !(cfg.flags & (MPM_FLAG_NAIVE | MPM_FLAG_DETERMINISTIC)) &&
+           (D == 2 ? p2g_cells_supported<2>(G) : p2g_cells_supported<3>(G));
+  if (deterministic) {
+    const long long nc = cfg.n_grid - 1;
+    det_cells = D == 2 ? nc * nc : nc * nc * nc;
+    det_key_bits = 1;
+    while ((1LL << det_key_bits) < det_cells) det_key_bits++;
+    if ((rc = dalloc(&det_rec, (size_t)cap * (D == 2 ? 8 : 16))) || (rc = dalloc(&det_cell_start, (size_t)det_cells + 2)))
+      return rc;
+  }
   // 2D only: in 3D the Jacobi-SVD-heavy kernels are compute-bound and fusing them costs occupancy (measured slower)
   fused = binned && D == 2 && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE));
   pipelined = fused || multi;
@@ -502,11 +525,14 @@ int mpm_handle::upload(const void *aos, const int *ids, long long count, int on_
 int mpm_handle::begin_resort() {
   int *ns = bin_start_buf[bs ^ 1];
   int *na = active_bins_buf[bs ^ 1];
-  MPM_CUDA(cudaMemsetAsync(ns, 0, ((size_t)G.n_bins + 4) * sizeof(int), stream));
-  if (D == 2) launch_count_rank<2>(P, G, s2[cur], n, (unsigned *)ns, sb.key[0], (unsigned *)sb.val[0], status_dev, stream, dev_ext);
-  else launch_count_rank<3>(P, G, s3[cur], n, (unsigned *)ns, sb.key[0], (unsigned *)sb.val[0], status_dev, stream, dev_ext);
-  // ns[k] = first slot of bin k; ns[n_bins] = live extent (dead slots sort behind every bin); ns[n_bins + 1] = n
-  exclusive_scan_u32((unsigned *)ns, (long long)G.n_bins + 2, sb.scan_tmp, stream);
+  const long long nc = n_cells();
+  MPM_CUDA(cudaMemsetAsync(cell_start, 0, ((size_t)nc + 4) * sizeof(int), stream));
+  if (D == 2) launch_count_rank<2>(P, G, s2[cur], n, (unsigned *)cell_start, sb.key[0], (unsigned *)sb.val[0], status_dev, stream, dev_ext);
+  else launch_count_rank<3>(P, G, s3[cur], n, (unsigned *)cell_start, sb.key[0], (unsigned *)sb.val[0], status_dev, stream, dev_ext);
+  // cell_start[c] = first slot of cell c (cells of a bin are consecutive); cell_start[nc] = live extent (dead slots
+  // sort behind every cell); cell_start[nc + 1] = n.  Every cpb-th entry is a bin start.
+  exclusive_scan_u32((unsigned *)cell_start, nc + 2, sb.scan_tmp, stream);
+  launch_bin_starts_from_cells(cell_start, G.n_bins, G.cpb, ns, stream);
   launch_active_bins(ns, G.n_bins, active_offs, sb.scan_tmp, na, stream);
   MPM_CUDA(cudaMemcpyAsync(&resort_host[0], active_offs + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
   MPM_CUDA(cudaMemcpyAsync(&resort_host[1], ns + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
@@ -616,8 +642,8 @@ int mpm_handle::rebin_storage() {
     int rc = begin_resort();
     if (rc) return rc;
     const int *ns = bin_start_buf[bs ^ 1];
-    if (D == 2) launch_reorder_scatter<2>(s2[cur], s2[cur ^ 1], 0, n, G.n_bins, ns, sb.key[0], (unsigned *)sb.val[0], stream, dev_ext);
-    else launch_reorder_scatter<3>(s3[cur], s3[cur ^ 1], 0, n, G.n_bins, ns, sb.key[0], (unsigned *)sb.val[0], stream, dev_ext);
+    if (D == 2) launch_reorder_scatter<2>(s2[cur], s2[cur ^ 1], 0, n, (int)n_cells(), cell_start, sb.key[0], (unsigned *)sb.val[0], stream, dev_ext);
+    else launch_reorder_scatter<3>(s3[cur], s3[cur ^ 1], 0, n, (int)n_cells(), cell_start, sb.key[0], (unsigned *)sb.val[0], stream, dev_ext);
     if (multi)  // the new extent (dead slots dropped) = first slot of the "dead" bin
       launch_slab_counters(dev_ext, nullptr, nullptr, nullptr, nullptr, 0, cap, ns + G.n_bins, stream);
     MPM_CUDA(cudaGetLastError());
@@ -703,7 +729,7 @@ int mpm_handle::step_grid_g2p(float dt) {
     else launch_grid_update<3>(P, dt, gp<3>(), stream);
   }
   // exact association everywhere under MPM_FLAG_STRICT and on the naive path (the bit-faithful modes)
-  const bool strict = (cfg.flags & (MPM_FLAG_STRICT | MPM_FLAG_NAIVE)) != 0;
+  const bool strict = (cfg.flags & (MPM_FLAG_STRICT | MPM_FLAG_NAIVE | MPM_FLAG_DETERMINISTIC)) != 0;
   if (multi) MPM_CUDA(cudaMemsetAsync(mig.count, 0, 8, stream));
   if (multi && !fast2d() && resort_due) {  // paths without the on-the-fly variant re-sort stand-alone, now
     int rc = rebin_storage();
@@ -735,7 +761,7 @@ int mpm_handle::step_grid_g2p(float dt) {
       sa.d = s2[cur ^ 1];
       sa.chunks = chunks_buf[bs];
       sa.n_chunks = n_chunks;
-      sa.new_start = bin_start_buf[bs ^ 1];
+      sa.new_start = cell_start;
       sa.key = sb.key[0];
       sa.rank = (const unsigned *)sb.val[0];
       sa.grid_in = grid;
@@ -773,7 +799,7 @@ int mpm_handle::step_grid_g2p(float dt) {
         gn.g = grid_next;
         launch_p2g_naive<2>(P, dt, s2[cur], n_binned, n, gn, status_dev, stream, dev_ext);
         if (resort)
-          launch_reorder_scatter<2>(s2[cur], s2[cur ^ 1], n_binned, n, G.n_bins, bin_start_buf[bs ^ 1], sb.key[0],
+          launch_reorder_scatter<2>(s2[cur], s2[cur ^ 1], n_binned, n, (int)n_cells(), cell_start, sb.key[0],
                                     (const unsigned *)sb.val[0], stream, dev_ext);
       } else {
         launch_g2p_naive<3>(P, dt, s3[cur], n_binned, n, gp<3>(), mig, status_dev, strict, stream, nullptr, dev_ext);
@@ -875,6 +901,31 @@ int mpm_handle::step_grid_g2p(float dt) {
   return MPM_OK;
 }
 
+// MPM_FLAG_DETERMINISTIC: stable sort of the storage by cell, then the fixed-order P2G (mpm_deterministic.cu)
+int mpm_handle::det_sort_and_p2g(float dt) {
+  if (n > 0) {
+    Phase ph(this, MPM_PHASE_BIN, 3 + 3 * ((det_key_bits + 7) / 8));
+    if (D == 2) launch_det_cell_keys<2>(P, s2[cur], n, sb.key[0], status_dev, stream);
+    else launch_det_cell_keys<3>(P, s3[cur], n, sb.key[0], status_dev, stream);
+    launch_iota(sb.val[0], n, stream);
+    const int r = radix_sort_pairs(sb, n, det_key_bits, stream);
+    launch_bin_starts(sb.key[r], n, (int)det_cells, det_cell_start, stream);
+    if (D == 2) launch_reorder<2>(s2[cur], s2[cur ^ 1], sb.val[r], n, stream);
+    else launch_reorder<3>(s3[cur], s3[cur ^ 1], sb.val[r], n, stream);
+    cur ^= 1;
+  } else {
+    MPM_CUDA(cudaMemsetAsync(det_cell_start, 0, ((size_t)det_cells + 2) * sizeof(int), stream));
+  }
+  Phase ph(this, MPM_PHASE_P2G, 2);
+  if (D == 2) launch_det_p2g<2>(P, dt, s2[cur], n, det_rec, det_cell_start, grid, nodes, stream);
+  else launch_det_p2g<3>(P, dt, s3[cur], n, det_rec, det_cell_start, grid, nodes, stream);
+  p2g_ready = true;
+  p2g_dt = dt;
+  grid_read = grid;
+  MPM_CUDA(cudaGetLastError());
+  return MPM_OK;
+}
+
 int mpm_handle::substep(float dt, int n_steps) {
   if (n_steps < 0) {
     err = "substep: n_steps < 0";
@@ -888,6 +939,11 @@ int mpm_handle::substep(float dt, int n_steps) {
   if (!(dt > 0)) dt = cfg.dt;
   for (int s = 0; s < n_steps; s++) {
     int rc;
+    if (deterministic) {
+      if ((rc = det_sort_and_p2g(dt))) return rc;
+      if ((rc = step_grid_g2p(dt))) return rc;
+      continue;
+    }
     const int every = current_interval();
     if (every > 0 && steps_since_sort >= every) {
       // the fast 2D kernel re-sorts on the fly inside this substep; every other path re-sorts stand-alone now

@@ -7,6 +7,7 @@ namespace mpm {
 
 struct BinGeom {
   int edge;      // cells per bin edge
+  int cpb;       // cells per bin = edge^dim
   int nb[3];     // bins per axis (x: over the owned slab)
   int n_bins;
   // bins that held particles at the last re-sort, compacted: the CTA-per-bin kernels launch one CTA per
@@ -80,6 +81,14 @@ struct Substep2dArgs {
 void launch_substep2d(const Substep2dArgs &a, bool flip, bool mig, bool resort, cudaStream_t st);
 int substep2d_chunk_capacity();  // particles per work-list entry (the kernel's shared-memory chunk)
 
+// ---- MPM_FLAG_DETERMINISTIC (mpm_deterministic.cu): fixed-order P2G without atomics ----
+template <int D>
+void launch_det_cell_keys(const Params &P, const SoA<D> &s, long long n, unsigned *key, int *status, cudaStream_t st);
+// records (8 | 16 floats per slot) + one thread per node summing its 3^d cells' particles in storage order
+template <int D>
+void launch_det_p2g(const Params &P, float dt, const SoA<D> &s, long long n, float *rec, const int *cell_start,
+                    float4 *grid, long long nodes, cudaStream_t st);
+
 // ---- AoS <-> SoA at the C-ABI ------------------------------------------------------------------
 // records [first, first+count) of the caller's AoS -> SoA slots [first, first+count), id = index
 template <int D>
@@ -111,7 +120,9 @@ struct SortBuffers {
 size_t sort_hist_elems(long long n);
 size_t scan_tmp_elems(long long n);
 int radix_sort_pairs(SortBuffers &B, long long n, int bits, cudaStream_t st);
-// storage re-sort by counting (see mpm_sort.cu): counts[n_bins+2] zeroed by the caller and scanned afterwards
+// storage re-sort by counting (see mpm_sort.cu): the key is the CELL inside the bin (bin * cpb + local cell), so the
+// storage is cell-ordered inside every bin; counts[n_bins*cpb + 2] zeroed by the caller and scanned afterwards;
+// launch_bin_starts_from_cells then takes every cpb-th entry as the bin ranges
 template <int D>
 void launch_count_rank(const Params &P, const BinGeom &G, const SoA<D> &s, long long n, unsigned *counts, unsigned *key,
                        unsigned *rank, int *status, cudaStream_t st, const int *dev_n = nullptr);
@@ -119,6 +130,7 @@ template <int D>
 void launch_reorder_scatter(const SoA<D> &src, const SoA<D> &dst, long long first, long long n, int n_bins,
                             const int *start, const unsigned *key, const unsigned *rank, cudaStream_t st,
                             const int *dev_n = nullptr);
+void launch_bin_starts_from_cells(const int *cell_start, int n_bins, int cpb, int *bin_start, cudaStream_t st);
 // bin_start[n_bins+1] from sorted keys
 void launch_bin_starts(const unsigned *sorted_key, long long n, int n_bins, int *bin_start, cudaStream_t st);
 void launch_iota(int *v, long long n, cudaStream_t st);

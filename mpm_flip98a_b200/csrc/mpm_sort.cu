@@ -18,6 +18,7 @@ BinGeom make_bin_geom(const Params &P, int dim, int edge) {
   G.nb[1] = (P.n_grid - 1 + edge - 1) / edge;
   G.nb[2] = dim == 3 ? G.nb[1] : 1;
   G.n_bins = G.nb[0] * G.nb[1] * G.nb[2];
+  G.cpb = dim == 3 ? edge * edge * edge : edge * edge;
   G.active = nullptr;
   G.n_active = 0;
   return G;
@@ -232,6 +233,15 @@ void launch_bin_starts(const unsigned *sorted_key, long long n, int n_bins, int 
   k_bin_starts<<<(unsigned)((n + 1 + 255) / 256), 256, 0, st>>>(sorted_key, n, n_bins, bin_start);
 }
 
+__global__ void k_bin_starts_from_cells(const int *__restrict__ cell_start, int n_bins, int cpb, int *__restrict__ bin_start) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= n_bins) bin_start[b] = cell_start[(size_t)b * cpb];
+  if (b == n_bins) bin_start[b + 1] = cell_start[(size_t)n_bins * cpb + 1];
+}
+void launch_bin_starts_from_cells(const int *cell_start, int n_bins, int cpb, int *bin_start, cudaStream_t st) {
+  k_bin_starts_from_cells<<<(unsigned)((n_bins + 1 + 255) / 256), 256, 0, st>>>(cell_start, n_bins, cpb, bin_start);
+}
+
 __global__ void k_flag_active(const int *__restrict__ bin_start, int n_bins, unsigned *__restrict__ offs) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b <= n_bins) offs[b] = (b < n_bins && bin_start[b + 1] > bin_start[b]) ? 1u : 0u;
@@ -251,11 +261,14 @@ void launch_active_bins(const int *bin_start, int n_bins, unsigned *offs, unsign
 // ------------------------------------------------------------------------------------------------
 // Storage re-sort by counting (the engine's periodic re-binning; mpm_bin_particles keeps the stable radix
 // sort above because ITS permutation is compared bit-exactly with the CPU binning oracle).
-// Particles are already nearly in bin order, so one pass suffices: every slot takes a rank inside its new
-// bin from a warp-aggregated counter (MATCH.ANY groups the lanes of a warp by key: about one atomic per
-// warp and key), the counters are scanned into bin starts, and the consumer -- k_reorder_scatter here, or
-// the substep kernel itself (RESORT) -- writes each particle to start[key] + rank in the other buffer.
-// 12 bytes of traffic per particle instead of three 16-byte radix passes.
+// Particles are already nearly in order, so one pass suffices: every slot takes a rank inside its new
+// CELL (key = bin * cells-per-bin + cell inside the bin) from a warp-aggregated counter (MATCH.ANY groups the
+// lanes of a warp by key: about one atomic per warp and key), the counters are scanned into cell starts (every
+// cpb-th of which is a bin start), and the consumer -- k_reorder_scatter here, or the substep kernel itself
+// (RESORT) -- writes each particle to start[key] + rank in the other buffer.  12 bytes of traffic per particle
+// instead of three 16-byte radix passes.  Ordering by cell INSIDE the bin is what makes the substep kernel's
+// grid gather coalesce: the lanes of a warp then read the same few node rows (the round-2 profile had the L1
+// data pipe at 78 % of its wavefront peak with bin-only order: ~12 sectors per gather instruction).
 // ------------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(256) k_count_rank(Params P, BinGeom G, SoA<D> s, long long n, unsigned *__restrict__ counts,
@@ -274,10 +287,16 @@ __global__ void __launch_bounds__(256) k_count_rank(Params P, BinGeom G, SoA<D> 
     const int bad = clamp_base<D>(P, base);
     const bool dead = P.multi && load_mat(s, i) == DEAD;
     if (bad && !dead) atomicOr(status, bad);
-    kk = (unsigned)((base[0] - P.slab_lo) / G.edge);
+    const int x0 = base[0] - P.slab_lo;
+    kk = (unsigned)(x0 / G.edge);
+    unsigned local = (unsigned)(x0 % G.edge);
 #pragma unroll
-    for (int k = 1; k < D; k++) kk = kk * (unsigned)G.nb[k] + (unsigned)(base[k] / G.edge);
-    if (dead) kk = (unsigned)G.n_bins;  // emigrated: behind every live particle, dropped by the consumer
+    for (int k = 1; k < D; k++) {
+      kk = kk * (unsigned)G.nb[k] + (unsigned)(base[k] / G.edge);
+      local = local * (unsigned)G.edge + (unsigned)(base[k] % G.edge);
+    }
+    kk = kk * (unsigned)G.cpb + local;
+    if (dead) kk = (unsigned)G.n_bins * (unsigned)G.cpb;  // emigrated: behind every live particle, dropped by the consumer
   }
   const unsigned lane = threadIdx.x & 31u;
   const unsigned m = __match_any_sync(0xffffffffu, kk);

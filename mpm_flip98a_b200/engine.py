@@ -20,6 +20,7 @@ FLAG_STRICT = 4
 FLAG_G2P_TILE = 8
 FLAG_NO_FUSE = 16
 FLAG_OVERLAP = 32
+FLAG_DETERMINISTIC = 64
 
 _ERRORS = {-1: "MPM_E_INVALID", -2: "MPM_E_CUDA", -3: "MPM_E_CAPACITY", -4: "MPM_E_DOMAIN", -5: "MPM_E_CFL",
            -6: "MPM_E_STATE"}
@@ -44,7 +45,7 @@ class Config(ctypes.Structure):
                 ("materials", Material * 4), ("capacity", ctypes.c_longlong), ("device", ctypes.c_int),
                 ("flags", ctypes.c_int), ("slab_lo", ctypes.c_int), ("slab_hi", ctypes.c_int),
                 ("stream", ctypes.c_void_p), ("bin_edge", ctypes.c_int), ("rebin_every", ctypes.c_int),
-                ("reserved", ctypes.c_int * 6)]
+                ("mig_records", ctypes.c_int), ("reserved", ctypes.c_int * 5)]
 
 
 class SlabDesc(ctypes.Structure):
