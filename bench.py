@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 
 METRIC = "particle-substeps/sec"
 SWIRL = 3.0  # peak speed of c4's initial cellular flow (scenes.swirl_velocity)
-WARM = {"c2": 3000, "c3": 2000, "c4": 2000, "c5": 1000}  # untimed substeps that put the scene in motion
+WARM = {"c1": 1000, "c2": 3000, "c3": 2000, "c4": 2000, "c5": 1000}  # untimed substeps that put the scene in motion
 FRAME = 10  # substeps per e2e call == the reference's int(frame_dt/dt), mls-mpm88-explained.cpp:217
 
 # algorithmic bytes per particle-substep, per kernel: P2G reads the full record;
@@ -45,6 +45,7 @@ ALGO = {2: dict(p2g=56, g2p=32 + 52, flip_extra=8), 3: dict(p2g=104, g2p=56 + 10
 
 WORKLOADS = {
     # name: (description, dim, n_grid, alpha, scene builder kwargs)
+    "c1": ("2D 80^2 grid, 3000 particles: the reference program as shipped (BASELINE configs[0])", 2, 80, 0.0),
     "c2": ("2D 512^2 three-material scene, ~1M particles (BASELINE configs[1])", 2, 512, 0.0),
     "c3": ("2D 2048^2 dam-break fluid, ~16M particles, FLIP alpha=0.95 (BASELINE configs[2])", 2, 2048, 0.95),
     "c4": ("2D 8192^2 pool, ~245M particles, three material bands (BASELINE configs[3])", 2, 8192, 0.0),
@@ -54,6 +55,8 @@ WORKLOADS = {
 
 # the GPU tests that cover each benchmarked configuration at full size (pytest -m gpu)
 PARITY_TESTS = {
+    "c1": "tests/test_gpu_parity.py::test_shipped_scene_one_warm_substep_vs_reference_golden (golden = the unmodified "
+          "reference) and ::test_1000_substeps_chaotic_scenes_within_reference_noise",
     "c2": "tests/test_gpu_parity.py::test_config2_one_warm_substep_full_size",
     "c3": "tests/test_gpu_fullsize.py::test_config3_full_size (+ _apic)",
     "c4": "tests/test_gpu_fullsize.py::test_config4_full_size: same scene, same warm-up, 1 substep <= 1e-5 (C: reference "
@@ -67,7 +70,9 @@ def build_scene(name, n_grid=None):
     from mpm_flip98a_b200 import scenes
     _, dim, n, alpha = WORKLOADS[name]
     n = n_grid or n
-    if name == "c2":
+    if name == "c1":  # the reference's own seeding (xorshift128, :191-196), from the committed golden fixture
+        p = np.load(os.path.join(ROOT, "tests", "golden", "shipped_scene.npz"))["step0"].copy()
+    elif name == "c2":
         p = scenes.three_blocks_2d(n, per_side=4)
     elif name == "c3":
         p = scenes.dam_break_2d(n, per_side=3, width=0.47)
@@ -140,6 +145,8 @@ def cpu_sample(name, max_seconds=20.0, threads=1):
     _, dim, n_full, alpha = WORKLOADS[name]
     n_small = {2: min(n_full, 1024), 3: min(n_full, 96)}[dim]
     p, dim, n, alpha, dt, vol = build_scene(name, n_small)
+    if name == "c1":
+        vol, dt = 1.0, 1e-4  # the shipped constants (:11, :18)
     P = make_params(dim=dim, n_grid=n, vol_p=vol, alpha=alpha)
     O.advance(P, dt, p, 20, threads=host_threads())  # a warm, moving state (not part of the measurement)
     t0 = time.perf_counter()
@@ -264,6 +271,8 @@ def main():
 
     descr, dim, n_grid, alpha = WORKLOADS[args.workload]
     p_np, dim, n_grid, alpha, dt, vol = build_scene(args.workload)
+    if args.workload == "c1":
+        vol, dt = 1.0, 1e-4  # the shipped constants (:11, :18); material = the shipped one (colour slot -> last entry)
     n = len(p_np)
     words = p_np.shape[1]
     host = torch.empty((n, words), dtype=torch.float32, pin_memory=True)  # pinned: e2e copies are async DMA

@@ -5,9 +5,11 @@
 // (:217-225) -- with advance() replaced by mpm_substep() on a B200 and the GUI / PNG writer replaced by a
 // headless point splat into binary PPM frames (no X11, no stb).  Plain C++14 + include/mpm.h.
 //
-//   mls_mpm88_driver [--steps N] [--frames DIR] [--dump FILE] [--three-blocks]
+//   mls_mpm88_driver [--steps N] [--frames DIR] [--dump FILE] [--three-blocks] [--devices 0,1,...]
 //
 // --dump writes the final 56-byte particle records (the reference's own struct layout) for the tests.
+// --devices runs the same loop on several GPUs (one x-slab per listed CUDA ordinal, a device may repeat) through
+// the mpm_group_* calls: same three statements -- upload, substep, read.
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -85,7 +87,12 @@ int main(int argc, char **argv) {
   int steps = 2500;  // :214
   std::string frames, dump;
   bool three = false;
+  std::vector<int> devices;
   for (int a = 1; a < argc; a++) {
+    if (!strcmp(argv[a], "--devices") && a + 1 < argc) {
+      for (char *t = strtok(argv[++a], ","); t; t = strtok(nullptr, ",")) devices.push_back(atoi(t));
+      continue;
+    }
     if (!strcmp(argv[a], "--steps") && a + 1 < argc) steps = atoi(argv[++a]);
     else if (!strcmp(argv[a], "--frames") && a + 1 < argc) frames = argv[++a];
     else if (!strcmp(argv[a], "--dump") && a + 1 < argc) dump = argv[++a];
@@ -105,6 +112,53 @@ int main(int argc, char **argv) {
   mpm_config cfg;
   mpm_default_config(&cfg, 2);  // the constants of :8-26
   cfg.capacity = (long long)particles.size();
+  if (!devices.empty()) {  // several GPUs behind one handle: the same loop
+    mpm_group *g = mpm_group_create(&cfg, devices.data(), (int)devices.size());
+    if (!g || mpm_group_upload_particles(g, particles.data(), (long long)particles.size()) != MPM_OK) {
+      fprintf(stderr, "group: %s\n", mpm_group_last_error(g));
+      return 1;
+    }
+    int frame = 0;
+    const int every = (int)(frame_dt / dt);  // :217
+    for (int step = 0; step < steps; step += every) {
+      const int k = steps - step < every ? steps - step : every;
+      if (mpm_group_substep(g, dt, k) != MPM_OK) {  // `every` x advance(dt), :215
+        fprintf(stderr, "substep: %s\n", mpm_group_last_error(g));
+        return 1;
+      }
+      if (!frames.empty()) {
+        mpm_group_read_particles(g, particles.data(), (long long)particles.size());
+        write_frame(frames, frame++, particles, 800);
+      }
+    }
+    if (mpm_group_read_particles(g, particles.data(), (long long)particles.size()) != MPM_OK) {
+      fprintf(stderr, "read: %s\n", mpm_group_last_error(g));
+      return 1;
+    }
+    const int st = mpm_group_poll_status(g);
+    double cx = 0, cy = 0, ke = 0;
+    for (const Particle &p : particles) {
+      cx += p.x[0];
+      cy += p.x[1];
+      ke += 0.5 * ((double)p.v[0] * p.v[0] + (double)p.v[1] * p.v[1]);
+    }
+    printf("steps %d particles %zu status %d com %.7f %.7f ke %.4f slabs %zu:", steps, particles.size(), st,
+           cx / particles.size(), cy / particles.size(), ke, devices.size());
+    for (int k = 0; k < (int)devices.size(); k++) {
+      int dev, lo, hi;
+      long long cnt;
+      mpm_group_slab(g, k, &dev, &lo, &hi, &cnt);
+      printf(" [gpu %d: columns %d..%d, %lld particles]", dev, lo, hi, cnt);
+    }
+    printf("\n");
+    if (!dump.empty())
+      if (FILE *f = fopen(dump.c_str(), "wb")) {
+        fwrite(particles.data(), sizeof(Particle), particles.size(), f);
+        fclose(f);
+      }
+    mpm_group_destroy(g);
+    return st == MPM_OK ? 0 : 2;
+  }
   mpm_handle *h = mpm_create(&cfg);
   if (!h) {
     fprintf(stderr, "mpm_create: %s\n", mpm_last_error(nullptr));

@@ -52,6 +52,11 @@ struct mpm_handle {
   // `grid`; the two swap each substep.  grid_read = the buffer that holds the last UPDATED grid (mpm_read_grid).
   float4 *grid_next = nullptr, *grid_read = nullptr;
   bool fused = false, p2g_ready = false;
+  // 2D default path: byte maps of the 8x8-node tiles each grid buffer was scattered into (k_grid_tiles); they travel
+  // with the buffers when these swap
+  unsigned char *touched_g = nullptr, *touched_n = nullptr;  // of `grid` / of `grid_next`
+  int tiles_x = 0, tiles_y = 0;
+  bool tiles_on() const { return touched_g != nullptr; }
   // overlapped slab schedule (MPM_FLAG_OVERLAP): the fused kernel of the bins >= 2 bin columns away from the slab
   // cuts runs on a side stream while the main stream finishes the boundary bins and the caller exchanges
   // emigrants / halo columns; act_lo_end / act_hi_begin split the (sorted) active-bin list into lo | interior | hi
@@ -415,6 +420,15 @@ int mpm_handle::init() {
   if (pipelined)
     if ((rc = dalloc(&grid_next, (size_t)nodes))) return rc;
   if (fast2d()) {
+    tiles_x = (P.ncol + 7) / 8;
+    tiles_y = (P.n1 + 7) / 8;
+    const size_t tb = (size_t)tiles_x * tiles_y;
+    if ((rc = dalloc(&touched_g, tb)) || (rc = dalloc(&touched_n, tb))) return rc;
+    MPM_CUDA(cudaMemsetAsync(touched_g, 0, tb, stream));
+    MPM_CUDA(cudaMemsetAsync(touched_n, 0, tb, stream));
+    // an unmarked tile must hold zeros
+    MPM_CUDA(cudaMemsetAsync(grid, 0, (size_t)nodes * sizeof(float4), stream));
+    MPM_CUDA(cudaMemsetAsync(grid_next, 0, (size_t)nodes * sizeof(float4), stream));
     // one entry per chunk: at most one per non-empty bin plus one per full chunk of particles
     chunks_cap = (long long)G.n_bins + cap / substep2d_chunk_capacity() + 2;
     for (int b = 0; b < 2; b++)
@@ -592,6 +606,13 @@ int mpm_handle::end_resort() {
 int mpm_handle::rebin_storage() {
   join_side();
   if (resort_pending) end_resort();
+  if (deterministic) {
+    // the counting re-sort ranks with atomics (its order inside a cell is not reproducible); this mode keeps the
+    // upload order and renews it with a STABLE sort by cell before every substep (det_sort_and_p2g)
+    steps_since_sort = 0;
+    n_binned = n;
+    return MPM_OK;
+  }
   if (binned && cfg.rebin_every == 0) {
     // Adaptive re-sort interval.  The binned kernels tolerate a particle that drifted up to MARGIN = 1 cell out of
     // its bin; beyond that it takes the per-particle scatter (correct, but as slow as the naive path), and once the
@@ -695,6 +716,7 @@ int mpm_handle::resident_p2g(float dt) {
     if (D == 2) launch_p2g_naive<2>(P, dt, s2[cur], 0, n, gp<2>(), status_dev, stream, dev_ext);
     else launch_p2g_naive<3>(P, dt, s3[cur], 0, n, gp<3>(), status_dev, stream, dev_ext);
   }
+  if (tiles_on()) MPM_CUDA(cudaMemsetAsync(touched_g, 1, (size_t)tiles_x * tiles_y, stream));  // written everywhere
   p2g_ready = true;  // `grid` holds P2G(dt) of the current particle state
   p2g_dt = dt;
   grid_read = grid;
@@ -725,8 +747,22 @@ int mpm_handle::step_grid_g2p(float dt) {
   }
   {
     Phase ph(this, MPM_PHASE_GRID, 1);
-    if (D == 2) launch_grid_update<2>(P, dt, gp<2>(), stream);
-    else launch_grid_update<3>(P, dt, gp<3>(), stream);
+    if (tiles_on()) {
+      // update of this substep's grid and reset of the next P2G target in one launch, touched tiles only
+      launch_grid_tiles(P, dt, grid, vold, touched_g, grid_next, touched_n, tiles_x, tiles_y, stream);
+      if (multi) {
+        // the two tile columns next to each cut: ghost sums, migrating particles and the immigrant tail land there
+        // through kernels that do not mark tiles themselves
+        const size_t col2 = (size_t)(tiles_x < 2 ? tiles_x : 2) * tiles_y;
+        if (cfg.slab_lo > 0) MPM_CUDA(cudaMemsetAsync(touched_n, 1, col2, stream));
+        if (cfg.slab_hi < cfg.n_grid)
+          MPM_CUDA(cudaMemsetAsync(touched_n + (size_t)tiles_x * tiles_y - col2, 1, col2, stream));
+      }
+    } else if (D == 2) {
+      launch_grid_update<2>(P, dt, gp<2>(), stream);
+    } else {
+      launch_grid_update<3>(P, dt, gp<3>(), stream);
+    }
   }
   // exact association everywhere under MPM_FLAG_STRICT and on the naive path (the bit-faithful modes)
   const bool strict = (cfg.flags & (MPM_FLAG_STRICT | MPM_FLAG_NAIVE | MPM_FLAG_DETERMINISTIC)) != 0;
@@ -736,7 +772,7 @@ int mpm_handle::step_grid_g2p(float dt) {
     if (rc) return rc;
   }
   if (fused) {
-    {
+    if (!tiles_on()) {
       Phase ph(this, MPM_PHASE_CLEAR, 0);
       MPM_CUDA(cudaMemsetAsync(grid_next, 0, (size_t)nodes * sizeof(float4), stream));  // :50 of the next substep
     }
@@ -767,6 +803,9 @@ int mpm_handle::step_grid_g2p(float dt) {
       sa.grid_in = grid;
       sa.vold_in = (const float2 *)vold;
       sa.grid_out = grid_next;
+      sa.touched_out = touched_n;
+      sa.tiles_x = tiles_x;
+      sa.tiles_y = tiles_y;
       sa.status = status_dev;
       sa.stats = stats_dev;
       sa.mig = mig;
@@ -851,6 +890,9 @@ int mpm_handle::step_grid_g2p(float dt) {
     float4 *t = grid;
     grid = grid_next;
     grid_next = t;
+    unsigned char *tt = touched_g;
+    touched_g = touched_n;
+    touched_n = tt;
     p2g_ready = true;  // ... up to migrating particles, which the x-slab exchange adds (slab_stage / slab_consume)
     p2g_dt = dt;
     if (prof_on) prof.fused_substeps++;

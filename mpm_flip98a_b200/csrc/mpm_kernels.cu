@@ -43,6 +43,59 @@ __global__ void __launch_bounds__(256) k_grid_update(Params P, float dt, float4 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 2D default path: grid update of one buffer AND reset of the other, restricted to the 8x8-node tiles that were
+// actually written.  Every kernel that scatters into a grid buffer marks the tiles it can touch in that buffer's
+// byte map (`touched`); a tile nobody marked holds zeros and needs neither the update (:109 skips empty nodes
+// anyway) nor the reset.  One launch replaces the memset of the whole grid (:50) plus the update pass over all
+// nodes: on the 8192^2 pool scene 58 % of the tiles are never touched.
+//   upd / t_upd : buffer that holds this substep's P2G sums -> (v, 1|0) in place; its marks stay (it is the buffer
+//                 that will be reset in the next substep)
+//   clr / t_clr : buffer the NEXT P2G will scatter into -> zeros, marks cleared
+// CTA = 8 node columns x 128 nodes (16 tiles), a warp per column: 512-byte coalesced segments.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_grid_tiles(Params P, float dt, float4 *__restrict__ upd, float2 *__restrict__ vold,
+                                                    const unsigned char *__restrict__ t_upd, float4 *__restrict__ clr,
+                                                    unsigned char *__restrict__ t_clr, int tiles_y) {
+  const int tx = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = tx * 8 + w;  // local node column
+  const int j0 = blockIdx.y * 128;
+  const bool flip = P.alpha != 0.0f;
+  unsigned char fu[4], fc[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const int ty = (j0 + r * 32) / 8 + lane / 8;
+    const bool in = ty < tiles_y;
+    fu[r] = in ? t_upd[tx * tiles_y + ty] : 0;
+    fc[r] = in && clr ? t_clr[tx * tiles_y + ty] : 0;
+  }
+  __syncthreads();  // every flag of this CTA's tiles has been read before any is cleared
+  if (i < P.ncol) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const int j = j0 + r * 32 + lane;
+      if (j >= P.n1) continue;
+      const long long nd = (long long)i * P.n1 + j;
+      if (fu[r]) {
+        const float4 g4 = upd[nd];
+        float g[4] = {g4.x, g4.y, g4.z, g4.w}, vo[3];
+        if (grid_node_update<2>(P, dt, i + P.slab_lo, j, 0, g, vo)) upd[nd] = make_float4(g[0], g[1], g[2], g[3]);
+        if (flip) vold[nd] = make_float2(vo[0], vo[1]);
+      }
+      if (fc[r]) clr[nd] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+  }
+  if (clr && w == 0 && lane < 16) {
+    const int ty = j0 / 8 + lane;
+    if (ty < tiles_y) t_clr[tx * tiles_y + ty] = 0;
+  }
+}
+void launch_grid_tiles(const Params &P, float dt, float4 *upd, void *vold, const unsigned char *t_upd, float4 *clr,
+                       unsigned char *t_clr, int tiles_x, int tiles_y, cudaStream_t st) {
+  dim3 grid((unsigned)tiles_x, (unsigned)((P.n1 + 127) / 128));
+  k_grid_tiles<<<grid, 256, 0, st>>>(P, dt, upd, (float2 *)vold, t_upd, clr, t_clr, tiles_y);
+}
+
 template <int D>
 void launch_grid_update(const Params &P, float dt, GridPtrs<D> g, cudaStream_t st) {
   unsigned blocks = (unsigned)((g.nodes + 255) / 256);
@@ -517,9 +570,11 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
     // ---- phase 2: thread per (cell, stencil row) ----
     const int n_items = item_first[NC];
     for (int item = tid; item < n_items * TPC; item += NT) {
-      // TPC == 3: a-major numbering (all items for row 0, then row 1, ...) keeps `a` warp-uniform
-      const int it = TPC == 1 ? item : item % n_items;
-      const int a_lo = TPC == 1 ? 0 : item / n_items, a_n = TPC == 1 ? 3 : 1;
+      // TPC == 3: the three stencil rows of an item sit in ADJACENT lanes, so their reads of the item's records are
+      // one shared-memory broadcast instead of three wavefronts from three warps (the 3D kernel was bound by the
+      // L1 data pipe: 77 % of its wavefront peak, 260 M bank conflicts); `a` is a per-lane value, selected below
+      const int it = TPC == 1 ? item : item / TPC;
+      const int a_lo = TPC == 1 ? 0 : item % TPC, a_n = TPC == 1 ? 3 : 1;
       const int cell = item_cell[it];
       int n0, n1;
       {
@@ -754,8 +809,11 @@ template void launch_g2p2g<3>(const Params &, const BinGeom &, float, float, con
 // ------------------------------------------------------------------------------------------------
 // NOTE: no min-blocks hint here on purpose: with one, ptxas front-loads all 3^D node loads (56 regs),
 // which measured 14% slower on B200 than the interleaved schedule it picks without (48 regs).
+#ifndef MPM_G2P3_MINB
+#define MPM_G2P3_MINB 6
+#endif
 template <int D, bool MIG, bool FAST, bool FLIP>
-__global__ void __launch_bounds__(128) k_g2p_naive(Params P, float dt, SoA<D> s, long long first, long long n,
+__global__ void __launch_bounds__(128, (D == 3 && FAST) ? MPM_G2P3_MINB : 1) k_g2p_naive(Params P, float dt, SoA<D> s, long long first, long long n,
                                                    const float4 *__restrict__ grid, const void *__restrict__ vold_,
                                                    MigPtrs mig, int *__restrict__ status,
                                                    unsigned long long *__restrict__ stats, const int *__restrict__ dev_n) {

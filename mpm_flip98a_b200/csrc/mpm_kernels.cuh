@@ -43,6 +43,9 @@ void launch_slab_counters(int *ext, const int *add_a, const int *add_b, const in
                           long long cap, const int *set_extent, cudaStream_t st);
 template <int D>
 void launch_grid_update(const Params &P, float dt, GridPtrs<D> g, cudaStream_t st);
+// 2D: update `upd` and reset `clr` on the tiles (8x8 nodes) their byte maps mark; see k_grid_tiles
+void launch_grid_tiles(const Params &P, float dt, float4 *upd, void *vold, const unsigned char *t_upd, float4 *clr,
+                       unsigned char *t_clr, int tiles_x, int tiles_y, cudaStream_t st);
 
 // ---- binned path: one CTA per bin, in-CTA cell sort + register accumulation (see mpm_kernels.cu) --
 template <int D>
@@ -74,6 +77,8 @@ struct Substep2dArgs {
   const float4 *grid_in;      // updated grid of this substep
   const float2 *vold_in;      // FLIP: pre-gravity node velocity
   float4 *grid_out;           // P2G target of the next substep (zeroed)
+  unsigned char *touched_out; // its tile map (8x8-node tiles, x-major, tiles_y per column): marked by every CTA
+  int tiles_x, tiles_y;
   int *status;
   unsigned long long *stats;
   MigPtrs mig;

@@ -83,7 +83,14 @@ __device__ __noinline__ bool emigrate2(const Params &P, const MigPtrs &mig, int 
 // a particle that drifted past the 1-cell bin margin since the last re-sort: plain per-particle scatter
 // with the reference's exact association (:92-100)
 __device__ __noinline__ void scatter_fallback(const Params &P, float4 *__restrict__ grid, int bx, int by, f2 fx, f2 mv,
-                                              M2c A) {
+                                              M2c A, unsigned char *__restrict__ touched, int tiles_y) {
+  {  // the tiles of the 3x3 nodes (at most four)
+    const int t0 = (bx - P.slab_lo) >> 3, t1 = (bx - P.slab_lo + 2) >> 3, u0 = by >> 3, u1 = (by + 2) >> 3;
+    touched[t0 * tiles_y + u0] = 1;
+    touched[t0 * tiles_y + u1] = 1;
+    touched[t1 * tiles_y + u0] = 1;
+    touched[t1 * tiles_y + u1] = 1;
+  }
   Stencil<2> st;
   st.base[0] = bx; st.base[1] = by;
   st.fx[0] = fx.x; st.fx[1] = fx.y;
@@ -127,6 +134,11 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
   float vmax = 0.0f;  // fastest particle of this thread (max norm): feeds the re-sort interval (CFL), see engine
   {
     if (tid < NC) cnt[tid] = 0;
+    if (tid < 9) {
+      // this CTA's REDs land on the nodes of cells [ox, ox+L) x [oy, oy+L): the 3x3 tiles around the bin's own
+      const int ttx = (work.w >> 16) - 1 + tid / 3, tty = (work.w & 0xffff) - 1 + tid % 3;
+      if (ttx >= 0 && ttx < A.tiles_x && tty >= 0 && tty < A.tiles_y) A.touched_out[ttx * A.tiles_y + tty] = 1;
+    }
     __syncthreads();
     // ---------------- phase 1: thread per particle (G2P of this substep, P2G record of the next) -------------
     PS nxt;
@@ -219,7 +231,7 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
         } else {
           cr[i] = 0xffffffffu;
           n_fallback++;
-          scatter_fallback(P, A.grid_out, bx, by, st.fx, mv, aff);
+          scatter_fallback(P, A.grid_out, bx, by, st.fx, mv, aff, A.touched_out, A.tiles_y);
         }
       }
     }

@@ -121,3 +121,19 @@ def test_checkpoint_restart_continues_the_run(tmp_path):
     e2.close()
     for k, (a, b) in {k: (fields(resumed, 2)[k], fields(straight, 2)[k]) for k in ("x", "v", "F")}.items():
         assert rel_l2(a, b) < 1e-4, k  # identical up to atomic summation order over 300 substeps
+
+
+@pytest.mark.gpu
+def test_cpp_driver_on_several_slabs(tmp_path, shipped):
+    """--devices: the same main() loop through mpm_group_* (several x-slabs behind one handle; here all on cuda:0)"""
+    build_driver()
+    dump = tmp_path / "p.bin"
+    out = subprocess.run([DRIVER, "--steps", "100", "--dump", str(dump), "--devices", "0,0,0"],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "slabs 3:" in out.stdout
+    p = np.fromfile(dump, np.float32).reshape(-1, 14)
+    want = shipped["step100"]
+    fw, fg = fields(want, 2), fields(p, 2)
+    assert rel_l2(fg["x"], fw["x"]) < 1e-4 and rel_l2(fg["v"], fw["v"]) < 2e-2
+    assert np.abs(p[:, 0:2].mean(0) - want[:, 0:2].mean(0)).max() < 1e-5
