@@ -223,7 +223,7 @@ def run_reference(args):
                     "d2h_bytes_per_step": 0},
             "host_cores_total": os.cpu_count(),
             "unmodified_reference_c1": unmodified_reference_c1()}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -376,7 +376,7 @@ def main():
                                 "note": "the reference is single-threaded as shipped; the threaded oracle is bitwise "
                                         "its serial self",
                                 "unmodified_reference_c1": unmodified_reference_c1()}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def motion_stats(sample, dim, n_grid, dt):
@@ -648,12 +648,23 @@ def run_slabs(args, rank, world, local):
                                                    "synchronisation%s" % (msg_bytes, ", overlapped with the interior bins"
                                                                           if overlap else ""),
                                        "exchange_bubble_ms_per_step": prof["exchange_bubble_ms_per_step"]})
-        print(json.dumps(line), flush=True)
+        emit(line)
     dist.barrier()
     dist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else this process or its libraries print (NCCL greets
+    with its version on stdout, the reference library's logger too) has been pointed at stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
     if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "--no-overlap" not in sys.argv:
         os.environ.setdefault("TORCH_NCCL_HIGH_PRIORITY", "1")
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the run (C libraries included)
     main()

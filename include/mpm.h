@@ -193,6 +193,7 @@ int mpm_bin_particles(mpm_handle *h, int *cell, int *key, int *order, int *bin_s
  * extent and the live-particle count stay on the device.
  *   rc = mpm_slab_begin(h, dt)   after an upload or a change of dt: P2G of the resident particles; returns 1 when
  *                                messages were staged (exchange them now), 0 when there is nothing to exchange
+ *                                (in particular when the run simply continues with the same dt)
  *   mpm_slab_step(h, dt)         consumes the received messages (ghost-column sums -- commutative, so both sides end
  *                                with bit-identical shared columns; immigrants appended, their P2G share added),
  *                                then one substep: grid update (shared columns redundantly) and G2P + the NEXT

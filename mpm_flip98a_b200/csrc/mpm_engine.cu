@@ -415,7 +415,10 @@ int mpm_handle::init() {
       return rc;
   }
   // 2D only: in 3D the Jacobi-SVD-heavy kernels are compute-bound and fusing them costs occupancy (measured slower)
-  fused = binned && D == 2 && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE));
+#ifndef MPM_FUSE_3D
+#define MPM_FUSE_3D 0
+#endif
+  fused = binned && (D == 2 || MPM_FUSE_3D) && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE));
   pipelined = fused || multi;
   if (pipelined)
     if ((rc = dalloc(&grid_next, (size_t)nodes))) return rc;
@@ -1199,12 +1202,16 @@ int mpm_handle::slab_consume() {
 int mpm_handle::slab_begin(float dt) {
   if (!multi) return 0;
   MPM_CUDA(cudaSetDevice(cfg.device));
-  if (p2g_ready && p2g_dt == dt && slab_state == SLAB_SETTLED) return 0;  // state complete, nothing to exchange
-  if (slab_state == SLAB_STAGED) {
-    err = "slab_begin: messages of the last substep are still outstanding (exchange them, then mpm_slab_settle)";
-    return MPM_E_STATE;
+  // a run that continues with the same dt has nothing to (re)compute: either the state is complete (SETTLED) or the
+  // messages of the last substep were staged and -- by the contract "exchange after every call" -- exchanged, and the
+  // next mpm_slab_step consumes them
+  if (p2g_ready && p2g_dt == dt && slab_state != SLAB_FRESH) return 0;
+  int rc;
+  if (slab_state == SLAB_STAGED) {  // dt changes mid-run: take in the outstanding messages, then redo the P2G
+    if ((rc = slab_consume())) return rc;
+    slab_state = SLAB_SETTLED;
   }
-  int rc = resident_p2g(dt);
+  rc = resident_p2g(dt);
   if (rc) return rc;
   MPM_CUDA(cudaMemsetAsync(mig.count, 0, 8, stream));  // nobody emigrates in a P2G
   if ((rc = slab_stage())) return rc;

@@ -752,7 +752,10 @@ template <int D, bool FAST, bool MIG, bool FUSED>
 static void launch_cells_variant(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, const int *bin_start,
                                  float4 *grid, int *status, unsigned long long *stats, const float4 *grid_in,
                                  const void *vold_in, float dt_g2p, MigPtrs mig, cudaStream_t st) {
-  if constexpr (FUSED && D == 3) {
+#ifndef MPM_FUSE_3D
+#define MPM_FUSE_3D 0
+#endif
+  if constexpr (FUSED && D == 3 && !MPM_FUSE_3D) {
     // never launched: the engine fuses in 2D only (in 3D the fused kernel loses more to register pressure than
     // it saves in traffic); not instantiating it keeps 1 KB-stack kernels out of the library
     (void)P; (void)G; (void)dt; (void)s; (void)bin_start; (void)grid; (void)status; (void)stats; (void)grid_in;

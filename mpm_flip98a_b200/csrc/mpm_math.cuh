@@ -291,14 +291,14 @@ MPM_HD Mat<3> rotation_of_svd(const Mat<3> &F) {
 }
 
 // Rotation factor for the 3D stress (the 3D lift has no counterpart in the reference; the CPU oracle defines it with
-// the very same statements, oracle/mpm_oracle.cpp rotation3): Newton's iteration for the polar decomposition,
-// X <- (X + X^-T) / 2 from X0 = F, converges quadratically to the rotation R of F = R S.  |X_{k+1} - X_k| <= 2e-4
-// means X_{k+1} is within ~2e-8 of R (below fp32 rounding): 2-3 iterations for snow (F within 2.5 % of a rotation
-// after the plastic clamp), 4-6 for a jelly under load, ~70 instructions each -- against ~1500 for the 4-sweep Jacobi
-// SVD whose U V^T it replaced in round 2 (the two agree to ~1e-6, tests/test_host_math.py).  Near-singular or
-// inverted F (det <= 1e-6 |F|^3) takes the SVD's U V^T.
-MPM_HD Mat<3> rotation_of(const Mat<3> &F) {
-  Mat<3> X = F;
+// the very same statements, oracle/mpm_oracle.cpp polar_newton3 / rotation3): Newton's iteration for the polar
+// decomposition, X <- (X + X^-T) / 2 from X0 = F, converges quadratically to the rotation R of F = R S.
+// |X_{k+1} - X_k| <= 2e-4 means X_{k+1} is within ~2e-8 of R (below fp32 rounding): 2-3 iterations for snow (F within
+// 2.5 % of a rotation after the plastic clamp), 3-4 for a jelly under load, ~70 instructions each -- against ~1500 for
+// the 4-sweep Jacobi SVD whose U V^T it replaced in round 2 (the two agree to ~1e-6, tests/test_host_math.py).
+// Returns false for a near-singular or inverted F (det <= 1e-6 |F|^3): the callers then take the SVD.
+MPM_HD bool polar_newton3(const Mat<3> &F, Mat<3> &X) {
+  X = F;
   float scale = 0.0f;
 #pragma unroll
   for (int c = 0; c < 3; c++)
@@ -312,7 +312,7 @@ MPM_HD Mat<3> rotation_of(const Mat<3> &F) {
     K.d[1][0] = c[1] * a[2] - c[2] * a[1]; K.d[1][1] = c[2] * a[0] - c[0] * a[2]; K.d[1][2] = c[0] * a[1] - c[1] * a[0];
     K.d[2][0] = a[1] * b[2] - a[2] * b[1]; K.d[2][1] = a[2] * b[0] - a[0] * b[2]; K.d[2][2] = a[0] * b[1] - a[1] * b[0];
     const float det = a[0] * K.d[0][0] + a[1] * K.d[0][1] + a[2] * K.d[0][2];
-    if (!(det > 1e-6f * scale * scale * scale)) return rotation_of_svd(F);
+    if (!(det > 1e-6f * scale * scale * scale)) return false;
     const float h = 0.5f / det;
     float delta = 0.0f;
 #pragma unroll
@@ -325,7 +325,107 @@ MPM_HD Mat<3> rotation_of(const Mat<3> &F) {
       }
     if (delta <= 2e-4f) break;
   }
-  return X;
+  return true;
+}
+MPM_HD Mat<3> rotation_of(const Mat<3> &F) {
+  Mat<3> X;
+  if (polar_newton3(F, X)) return X;
+  return rotation_of_svd(F);
+}
+
+// Device: reciprocal square root / division by the special-function unit (<= 2 ulp) inside the Jacobi rotations of
+// plastic_project3 -- a rotation angle that is off by an ulp leaves an off-diagonal of ~1e-7 |apq| behind, far below
+// what the next sweep tests for.  Host (tests/host_check.cpp): the oracle's exact statements.
+#if defined(__CUDA_ARCH__)
+#define MPM_RSQRT(x) rsqrtf(x)
+#define MPM_FDIV(a, b) __fdividef((a), (b))
+#define MPM_SQRT_POS(x) ((x) * rsqrtf(x))
+#else
+#define MPM_RSQRT(x) (1.0f / sqrtf(x))
+#define MPM_FDIV(a, b) ((a) / (b))
+#define MPM_SQRT_POS(x) sqrtf(x)
+#endif
+MPM_HD float dot3f(const float *a, const float *b) { return fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0])); }
+
+// One Jacobi rotation of the symmetric 3x3 (diagonal app, aqq; off-diagonal apq; arp, arq = the entries that couple
+// the third index) with the eigenvector columns p, q of V.  Returns whether it rotated.
+MPM_HD bool jacobi_rotate3(float &app, float &aqq, float &apq, float &arp, float &arq, float *vp, float *vq) {
+  if (!(fabsf(apq) > 6e-8f * (fabsf(app) + fabsf(aqq)))) return false;
+  const float h = 0.5f * (aqq - app);
+  const float t = MPM_FDIV(apq, h + copysignf(MPM_SQRT_POS(fmaf(h, h, apq * apq)), h));
+  const float c = MPM_RSQRT(fmaf(t, t, 1.0f)), s = t * c;
+  app = fmaf(-t, apq, app);
+  aqq = fmaf(t, apq, aqq);
+  apq = 0.0f;
+  const float x = arp, y = arq;
+  arp = fmaf(c, x, -(s * y));
+  arq = fmaf(s, x, c * y);
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const float a = vp[k], b = vq[k];
+    vp[k] = fmaf(c, a, -(s * b));
+    vq[k] = fmaf(s, a, c * b);
+  }
+  return true;
+}
+
+// Plastic projection of snow in 3D (:165-178 lifted): clamps the singular values of F to [lo, hi] and returns
+// det(F) / det(F') for the Jp update (:175).  Same structure as the reference's 2x2 svd (taichi.h:8389-8420: polar
+// decomposition first, then Jacobi rotations that diagonalise the symmetric factor):
+//   F = R S (polar_newton3),  S = V diag(l) V^T (cyclic Jacobi),  F' = R V diag(clamp(l)) V^T.
+// When Gershgorin's discs already place every eigenvalue of S inside [lo, hi] nothing is clamped: F stays, ratio 1.
+// Near-singular or inverted F takes the one-sided Jacobi SVD.  Statement for statement oracle/mpm_oracle.cpp
+// plastic_project3 (the definition; the reference has no 3D code).  `R_out` (optional) receives the rotation factor
+// of F' -- the R the next P2G's stress needs (:75-76), free here.
+MPM_HD float plastic_project3(float lo, float hi, Mat<3> &F, Mat<3> *R_out = nullptr) {
+  Mat<3> R;
+  if (!polar_newton3(F, R)) {
+    Mat<3> U, V;
+    float sg[3];
+    svd3(F, U, sg, V);
+    Mat<3> sig = mat_zero<3>();
+#pragma unroll
+    for (int i = 0; i < 3; i++) sig.d[i][i] = clampf(sg[i], lo, hi);
+    const float oldJ = mat_det(F);
+    F = mat_mul<3>(mat_mul<3>(U, sig), mat_transposed<3>(V));
+    if (R_out) *R_out = mat_mul<3>(U, mat_transposed<3>(V));
+    return oldJ / mat_det(F);
+  }
+  if (R_out) *R_out = R;
+  float a00 = dot3f(R.d[0], F.d[0]), a11 = dot3f(R.d[1], F.d[1]), a22 = dot3f(R.d[2], F.d[2]);
+  float a01 = 0.5f * (dot3f(R.d[0], F.d[1]) + dot3f(R.d[1], F.d[0]));
+  float a02 = 0.5f * (dot3f(R.d[0], F.d[2]) + dot3f(R.d[2], F.d[0]));
+  float a12 = 0.5f * (dot3f(R.d[1], F.d[2]) + dot3f(R.d[2], F.d[1]));
+  {
+    const float r0 = fabsf(a01) + fabsf(a02), r1 = fabsf(a01) + fabsf(a12), r2 = fabsf(a02) + fabsf(a12);
+    if (a00 - r0 >= lo && a00 + r0 <= hi && a11 - r1 >= lo && a11 + r1 <= hi && a22 - r2 >= lo && a22 + r2 <= hi) return 1.0f;
+  }
+  Mat<3> V = mat_diag<3>(1.0f);
+#pragma unroll 1
+  for (int sweep = 0; sweep < 6; sweep++) {
+    bool rotated = jacobi_rotate3(a00, a11, a01, a02, a12, V.d[0], V.d[1]);
+    rotated |= jacobi_rotate3(a00, a22, a02, a01, a12, V.d[0], V.d[2]);
+    rotated |= jacobi_rotate3(a11, a22, a12, a01, a02, V.d[1], V.d[2]);
+    if (!rotated) break;
+  }
+  const float l0 = clampf(a00, lo, hi), l1 = clampf(a11, lo, hi), l2 = clampf(a22, lo, hi);
+  float w0[3], w1[3], w2[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    w0[k] = l0 * V.d[0][k];
+    w1[k] = l1 * V.d[1][k];
+    w2[k] = l2 * V.d[2][k];
+  }
+  Mat<3> S;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = i; j < 3; j++) S.d[j][i] = S.d[i][j] = fmaf(w2[i], V.d[2][j], fmaf(w1[i], V.d[1][j], w0[i] * V.d[0][j]));
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int k = 0; k < 3; k++) F.d[j][k] = fmaf(R.d[2][k], S.d[j][2], fmaf(R.d[1][k], S.d[j][1], R.d[0][k] * S.d[j][0]));
+  return (a00 * a11 * a22) / (l0 * l1 * l2);
 }
 
 
@@ -501,15 +601,6 @@ MPM_HD void plastic_project(const Material &mat, Mat<2> &F) {
   sig.d[1][1] = clampf(sig.d[1][1], mat.sig_lo, mat.sig_hi);
   F = mat_mul<2>(mat_mul<2>(U, sig), mat_transposed<2>(V));
 }
-MPM_HD void plastic_project(const Material &mat, Mat<3> &F) {
-  Mat<3> U, V;
-  float sg[3];
-  svd3(F, U, sg, V);
-  Mat<3> sig = mat_zero<3>();
-#pragma unroll
-  for (int i = 0; i < 3; i++) sig.d[i][i] = clampf(sg[i], mat.sig_lo, mat.sig_hi);
-  F = mat_mul<3>(mat_mul<3>(U, sig), mat_transposed<3>(V));
-}
 // fluid keeps only the volume change: F <- J^(1/d) * I
 MPM_HD void fluid_project(Mat<2> &F) { F = mat_diag<2>(sqrtf(mat_det(F))); }
 MPM_HD void fluid_project(Mat<3> &F) { F = mat_diag<3>(cbrtf(mat_det(F))); }
@@ -529,9 +620,14 @@ MPM_HD void g2p_finish(const Params &P, const Material &mat, float dt, float *x,
   }
   Mat<D> Fn = mat_mul<D>(mat_add<D>(mat_diag<D>(1.0f), mat_scale<D>(dt, C)), F);  // :162
   if (mat.kind == KIND_SNOW) {
-    float oldJ = mat_det(Fn);  // :172 (F not yet rebuilt)
-    plastic_project(mat, Fn);
-    Jp = clampf(Jp * oldJ / mat_det(Fn), P.jp_min, P.jp_max);  // :175
+    if constexpr (D == 2) {
+      float oldJ = mat_det(Fn);  // :172 (F not yet rebuilt)
+      plastic_project(mat, Fn);
+      Jp = clampf(Jp * oldJ / mat_det(Fn), P.jp_min, P.jp_max);  // :175
+    } else {
+      const float ratio = plastic_project3(mat.sig_lo, mat.sig_hi, Fn);  // det(F) / det(F'), :172-175
+      Jp = clampf(Jp * ratio, P.jp_min, P.jp_max);
+    }
     F = Fn;
   } else if (mat.kind == KIND_JELLY) {
     F = Fn;

@@ -357,6 +357,9 @@ class Group:
     def poll_status(self):
         return self.lib.mpm_group_poll_status(self.g)
 
+    def synchronize(self):
+        self._check(self.lib.mpm_group_synchronize(self.g))
+
     def slabs(self):
         out = []
         for k in range(self.n_slabs):

@@ -163,6 +163,13 @@ class Oracle:
         self.lib.oracle_rotation3(m.ctypes.data_as(ctypes.c_void_p), R.ctypes.data_as(ctypes.c_void_p))
         return R
 
+    def plastic_project3(self, lo, hi, m):
+        """-> (F', det F / det F') of the 3D snow projection (oracle/mpm_oracle.cpp plastic_project3)"""
+        m = np.ascontiguousarray(m, np.float32).copy()
+        self.lib.oracle_plastic_project3.restype = ctypes.c_float
+        r = self.lib.oracle_plastic_project3(ctypes.c_float(lo), ctypes.c_float(hi), m.ctypes.data_as(ctypes.c_void_p))
+        return m, float(r)
+
     def svd3(self, m):
         m = np.ascontiguousarray(m, np.float32)
         U, V = np.zeros(9, np.float32), np.zeros(9, np.float32)

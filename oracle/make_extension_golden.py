@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE ONLY.  These parts have no counterpart in the reference ("parity
 unpinned"), so the fixture does not pin them to the reference -- it pins them to THEMSELVES: any later edit of
 oracle/mpm_oracle.cpp that changes their arithmetic (as the 3D Jacobi convergence rule did in round 1, and the
-Newton-polar rotation of the 3D stress in round 2: 120 substeps of the 3D cases moved by 2e-7 relative in x and 6e-5 in v) has to
+Newton-polar rotation of the 3D stress and the polar + symmetric-Jacobi snow projection in round 2: 120 substeps of the 3D cases
+moved by 2e-6 relative in x and 2e-4 in v, the growth of ~1e-7 per-substep differences in a collapsing pile) has to
 regenerate this file on purpose.  Run:  make -C oracle && python oracle/make_extension_golden.py
 """
 import os
@@ -43,6 +44,11 @@ def run():
     out["svd3_in"] = ms
     out["svd3_out"] = np.stack([np.concatenate(O.svd3(m)) for m in ms])
     out["rotation3_out"] = np.stack([O.rotation3(m) for m in ms])
+    lo, hi = np.float32(1 - 2.5e-2), np.float32(1 + 7.5e-3)
+    ms2 = (np.eye(3).reshape(1, 9) + 0.02 * rs.randn(64, 9)).astype(np.float32)  # around the clamp window
+    out["project3_in"] = ms2
+    out["project3_out"] = np.stack([np.concatenate([f, [r]]).astype(np.float32)
+                                    for f, r in (O.plastic_project3(lo, hi, m) for m in ms2)])
     return out
 
 

@@ -267,6 +267,14 @@ void hostcheck_rotation3(const float *m, float *R_svd, float *R_newton) {
   std::memcpy(R_svd, &a, 36);
   std::memcpy(R_newton, &b, 36);
 }
+float hostcheck_plastic_project3(float lo, float hi, float *m, float *R) {
+  Mat<3> M, r;
+  std::memcpy(&M, m, 36);
+  const float ratio = plastic_project3(lo, hi, M, &r);
+  std::memcpy(m, &M, 36);
+  std::memcpy(R, &r, 36);
+  return ratio;
+}
 void hostcheck_svd3(const float *m, float *U, float *sig3, float *V) {
   Mat<3> M, u, v;
   std::memcpy(&M, m, 36);

@@ -151,3 +151,28 @@ def test_group_handle_drives_slabs_from_the_c_abi(oracle, shipped, n_slabs):
     oracle.advance(make_params(), 1e-4, ref, 151)
     b0, b1 = scenes.bulk(ref, 2), scenes.bulk(later, 2)
     assert np.abs(b0["com"] - b1["com"]).max() <= 2e-3 * np.abs(b0["com"]).max()  # chaotic scene: reorder noise
+
+
+@pytest.mark.parametrize("flags", [0, FLAG_NO_FUSE])
+def test_run_continues_unsettled_and_changes_dt(oracle, flags):
+    """The calling pattern of bench.py / a long run: step_local(..., settle=False) several times in a row (the second
+    mpm_slab_begin finds staged-and-exchanged messages and must simply carry on), then a change of dt mid-run
+    (mpm_slab_begin takes in the outstanding messages and redoes the P2G).  Against one handle doing the same."""
+    p = scenes.jelly_drop()
+    p[:, 2] = 6.0
+    with mpm.Engine(dim=2, n_grid=80, capacity=len(p), flags=flags) as e:
+        e.upload(p)
+        e.substep(60, dt=1e-4)
+        e.substep(40, dt=5e-5)
+        single = e.read()
+    ranks, ex, slabs = parallel.make_local_cluster(mpm.Engine, p, 2, 80, 3, flags=flags, rebin_every=9)
+    parallel.step_local(ranks, ex, 25, dt=1e-4, settle=False)
+    parallel.step_local(ranks, ex, 35, dt=1e-4, settle=False)
+    parallel.step_local(ranks, ex, 40, dt=5e-5)
+    got = parallel.collect_local(ranks, len(p), p.shape[1])
+    assert [r.e.poll_status() for r in ranks] == [0, 0, 0] and sum(r.e.count for r in ranks) == len(p)
+    for r in ranks:
+        r.e.close()
+    assert rel_l2(got[:, 0:2], single[:, 0:2]) <= 1e-4 and rel_l2(got[:, 2:4], single[:, 2:4]) <= 1e-3
+    b0, b1 = scenes.bulk(single, 2), scenes.bulk(got, 2)
+    assert abs(b0["ke"] - b1["ke"]) <= 1e-3 * b0["ke"]

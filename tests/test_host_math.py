@@ -151,3 +151,54 @@ def test_polar3_newton_matches_svd_rotation(hc):
     for F in (np.diag([1.0, 1.0, -0.5]), np.diag([1.0, 0.0, 1.0]), np.zeros((3, 3)), 1e-4 * np.ones((3, 3))):
         a, b = rot(F.T.reshape(-1))
         assert np.array_equal(bits(a), bits(b))      # fallback path == the SVD rotation itself
+
+
+def test_plastic_project3_matches_svd_clamp(hc, oracle):
+    """The 3D snow projection (polar + symmetric Jacobi, oracle/mpm_oracle.cpp plastic_project3 == csrc/mpm_math.cuh):
+    host build BITWISE the oracle; against a float64 SVD clamp <= 2e-6; the returned R is the rotation factor of F';
+    untouched when every singular value is already inside the window; inverted F takes the SVD fallback."""
+    rs = np.random.RandomState(5)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    hc.lib.hostcheck_plastic_project3.restype = ctypes.c_float
+    lo, hi = np.float32(1 - 2.5e-2), np.float32(1 + 7.5e-3)
+
+    def random_rotation():
+        q, r = np.linalg.qr(rs.randn(3, 3))
+        q = q * np.sign(np.diag(r))
+        if np.linalg.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        return q
+
+    worst, untouched = 0.0, 0
+    for k in range(3000):
+        U, V = random_rotation(), random_rotation()
+        if k % 3 == 0:
+            sig = rs.uniform(0.96, 1.02, 3)                  # around the window: some clamped, some not
+        elif k % 3 == 1:
+            sig = rs.uniform(0.98, 1.005, 3)                 # inside: nothing to clamp
+        else:
+            sig = np.exp(rs.uniform(-1.0, 0.7, 3))           # far outside
+        F = ((U * sig) @ V.T).astype(np.float32)
+        m = np.ascontiguousarray(F.T.reshape(-1))            # column-major storage
+        mo, ro = oracle.plastic_project3(lo, hi, m)
+        mh, R = m.copy(), np.zeros(9, np.float32)
+        rh = hc.lib.hostcheck_plastic_project3(ctypes.c_float(lo), ctypes.c_float(hi), vp(mh), vp(R))
+        assert np.array_equal(bits(mo), bits(mh)) and bits(np.float32(ro)) == bits(np.float32(rh))
+        u, s, vt = np.linalg.svd(F.astype(np.float64))
+        want = (u * np.clip(s, lo, hi)) @ vt
+        got = mh.reshape(3, 3).T.astype(np.float64)
+        worst = max(worst, float(np.abs(got - want).max()))
+        assert abs(rh - np.prod(s) / np.prod(np.clip(s, lo, hi))) <= 3e-6 * max(1.0, rh)
+        Rm = R.reshape(3, 3).T.astype(np.float64)
+        assert np.abs(Rm - u @ vt).max() < 3e-6
+        if np.array_equal(bits(mh), bits(m)):
+            untouched += 1
+            assert rh == 1.0 and s.min() >= lo - 1e-6 and s.max() <= hi + 1e-6
+    assert worst < 2e-6, worst
+    assert untouched > 300, untouched                        # the early-out is exercised
+    F = np.diag([1.0, 1.0, -0.5]).astype(np.float32)         # inverted: SVD fallback, bitwise the oracle's
+    m = np.ascontiguousarray(F.T.reshape(-1))
+    mo, ro = oracle.plastic_project3(lo, hi, m)
+    mh, R = m.copy(), np.zeros(9, np.float32)
+    hc.lib.hostcheck_plastic_project3(ctypes.c_float(lo), ctypes.c_float(hi), vp(mh), vp(R))
+    assert np.array_equal(bits(mo), bits(mh)) and np.isfinite(mh).all()

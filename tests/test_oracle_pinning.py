@@ -143,6 +143,10 @@ def test_oracle_extensions_are_frozen(oracle):
     assert np.array_equal(bits(got), bits(gold["svd3_out"]))
     got = np.stack([oracle.rotation3(m) for m in gold["svd3_in"]])
     assert np.array_equal(bits(got), bits(gold["rotation3_out"]))
+    lo, hi = np.float32(1 - 2.5e-2), np.float32(1 + 7.5e-3)
+    got = np.stack([np.concatenate([f, [r]]).astype(np.float32)
+                    for f, r in (oracle.plastic_project3(lo, hi, m) for m in gold["project3_in"])])
+    assert np.array_equal(bits(got), bits(gold["project3_out"]))
 
 
 def test_rotation3_properties(oracle):

@@ -55,8 +55,9 @@ e = FakeEngine(n, slabs[rank])
 e.upload_ids(rec, ids)
 r = parallel.SlabRank(e, rank, world, "cpu")
 ex = parallel.DistExchange(r)
-parallel.step_dist(r, ex, 25)
-parallel.step_dist(r, ex, 15)   # a second call continues from the settled state without a begin-exchange
+parallel.step_dist(r, ex, 10, settle=False)
+parallel.step_dist(r, ex, 15, settle=False)  # continues an UNSETTLED run (messages staged and exchanged): no begin
+parallel.step_dist(r, ex, 15)                # ... and settles at the end
 grids = e.complete_grids
 rec, ids = e.read_ids()
 np.savez(sys.argv[3] + ".%d.npz" % rank, rec=rec, ids=ids, grid=np.stack(grids), lo=slabs[rank][0])
