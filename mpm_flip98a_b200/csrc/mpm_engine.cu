@@ -223,6 +223,11 @@ struct mpm_handle {
   int begin_resort();
   int end_resort();
   bool fast2d() const { return fused && D == 2 && !(cfg.flags & MPM_FLAG_STRICT); }
+  // 3D default: P2G (k_p2g_cells) and G2P (k_g2p3, mpm_substep3d.cu) stay separate kernels; the G2P re-sorts on the fly
+  bool fast3d() const {
+    return binned && D == 3 && !fused && !(cfg.flags & (MPM_FLAG_STRICT | MPM_FLAG_G2P_TILE));
+  }
+  bool resorts_on_the_fly() const { return fast2d() || fast3d(); }
   void carve(int b);
   int substep(float dt, int n_steps);
   int step_p2g(float dt);
@@ -770,7 +775,7 @@ int mpm_handle::step_grid_g2p(float dt) {
   // exact association everywhere under MPM_FLAG_STRICT and on the naive path (the bit-faithful modes)
   const bool strict = (cfg.flags & (MPM_FLAG_STRICT | MPM_FLAG_NAIVE | MPM_FLAG_DETERMINISTIC)) != 0;
   if (multi) MPM_CUDA(cudaMemsetAsync(mig.count, 0, 8, stream));
-  if (multi && !fast2d() && resort_due) {  // paths without the on-the-fly variant re-sort stand-alone, now
+  if (multi && !resorts_on_the_fly() && resort_due) {  // paths without the on-the-fly variant re-sort stand-alone, now
     int rc = rebin_storage();
     if (rc) return rc;
   }
@@ -904,7 +909,42 @@ int mpm_handle::step_grid_g2p(float dt) {
       Phase ph(this, MPM_PHASE_CLEAR, 0);
       MPM_CUDA(cudaMemsetAsync(grid_next, 0, (size_t)nodes * sizeof(float4), stream));  // :50 of the next substep
     }
-    {
+    // 3D default: the G2P kernel of mpm_substep3d.cu; a due re-sort rides on it (RESORT variant): first half here,
+    // the kernel is the consumer, second half after it has been enqueued
+    const bool fast3 = fast3d();
+    const bool resort3 = fast3 && resort_due && n > 0;
+    if (resort3) {
+      fused_resort_now = true;
+      int rc = rebin_storage();
+      fused_resort_now = false;
+      if (rc) return rc;
+    }
+    if (fast3) {
+      Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
+      G2p3Args ga;
+      ga.P = P;
+      ga.dt = dt;
+      ga.s = s3[cur];
+      ga.d = s3[cur ^ 1];
+      ga.first = 0;
+      ga.n = n;
+      ga.grid = grid;
+      ga.vold = (const float4 *)vold;
+      ga.new_start = cell_start;
+      ga.key = sb.key[0];
+      ga.rank = (const unsigned *)sb.val[0];
+      ga.mig = mig;
+      ga.status = status_dev;
+      ga.stats = stats_dev;
+      ga.dev_n = dev_ext;
+      launch_g2p3(ga, P.alpha != 0.0f, mig.enabled != 0, resort3, stream);
+      if (resort3) {
+        if (multi)  // the new extent (dead slots dropped) = first slot of the "dead" bin of the new order
+          launch_slab_counters(dev_ext, nullptr, nullptr, nullptr, nullptr, 0, cap, bin_start_buf[bs ^ 1] + G.n_bins, stream);
+        int rc = end_resort();
+        if (rc) return rc;
+      }
+    } else {
       Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
       if (binned && (cfg.flags & MPM_FLAG_G2P_TILE)) {
         if (D == 2) launch_g2p_bins<2>(P, G, dt, s2[cur], n_binned, bin_start, gp<2>(), mig, status_dev, strict, stream);
@@ -992,7 +1032,7 @@ int mpm_handle::substep(float dt, int n_steps) {
     const int every = current_interval();
     if (every > 0 && steps_since_sort >= every) {
       // the fast 2D kernel re-sorts on the fly inside this substep; every other path re-sorts stand-alone now
-      if (fast2d() && n > 0) resort_due = true;
+      if (resorts_on_the_fly() && n > 0) resort_due = true;
       else if ((rc = rebin_storage())) return rc;
     }
     if ((rc = step_p2g(dt))) return rc;

@@ -1,0 +1,80 @@
+// mpm_gather3.cuh -- the separable 3D G2P gather shared by the 3D kernels (mpm_kernels.cu, mpm_substep3d.cu).
+#pragma once
+#include "mpm_common.cuh"
+#include "mpm_math2.cuh"
+
+namespace mpm {
+
+// Fast 3D gather (:147-156 lifted to 27 nodes) in separable form, (x,y) components as packed pairs:
+//   t_ab = sum_c wz_c g_abc, u_ab = sum_c (wz_c dz_c) g_abc;   T_a = sum_b wy_b t_ab, Uy_a = sum_b (wy_b dy_b) t_ab,
+//   Uz_a = sum_b wy_b u_ab;   v += wx_a T_a, C.col0 += (wx_a dx_a) T_a, C.col1 += wx_a Uy_a, C.col2 += wx_a Uz_a
+// ~190 instructions instead of ~680 for the node-by-node form; fused multiply-adds, algebraically identical
+// (~1e-7 relative from the reference association; MPM_FLAG_STRICT / MPM_FLAG_NAIVE keep g2p_accumulate).
+// C comes back without the constant 4*inv_dx; with FLIP, dv = v - sum w vold.
+__device__ __forceinline__ void gather3_fast(const Params &P, const Stencil<3> &st, const float4 *__restrict__ grid,
+                                             const float4 *__restrict__ vold, bool flip, float *v, Mat<3> &C, float *dv) {
+  float wd[3][3];  // w * (k - fx) per axis
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) wd[k][ax] = st.w[k][ax] * ((float)k - st.fx[ax]);
+  f2 vxy = sp2(0.0f), c0xy = sp2(0.0f), c1xy = sp2(0.0f), c2xy = sp2(0.0f), oxy = sp2(0.0f);
+  float vz = 0.0f, c0z = 0.0f, c1z = 0.0f, c2z = 0.0f, oz = 0.0f;
+  const long long n1 = P.n1;
+  const long long node0 = ((long long)(st.base[0] - P.slab_lo) * n1 + st.base[1]) * n1 + st.base[2];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    f2 Txy = sp2(0.0f), Uyxy = sp2(0.0f), Uzxy = sp2(0.0f), Oxy = sp2(0.0f);
+    float Tz = 0.0f, Uyz = 0.0f, Uzz = 0.0f, Oz = 0.0f;
+#pragma unroll
+    for (int b = 0; b < 3; b++) {
+      const float4 *row = grid + node0 + (a * n1 + b) * n1;
+      const float4 g0 = __ldg(row), g1 = __ldg(row + 1), g2 = __ldg(row + 2);
+      f2 txy = mul2(sp2(st.w[0][2]), mk2(g0.x, g0.y));
+      txy = fma2(sp2(st.w[1][2]), mk2(g1.x, g1.y), txy);
+      txy = fma2(sp2(st.w[2][2]), mk2(g2.x, g2.y), txy);
+      const float tz = fmaf(st.w[2][2], g2.z, fmaf(st.w[1][2], g1.z, st.w[0][2] * g0.z));
+      f2 uxy = mul2(sp2(wd[0][2]), mk2(g0.x, g0.y));
+      uxy = fma2(sp2(wd[1][2]), mk2(g1.x, g1.y), uxy);
+      uxy = fma2(sp2(wd[2][2]), mk2(g2.x, g2.y), uxy);
+      const float uz = fmaf(wd[2][2], g2.z, fmaf(wd[1][2], g1.z, wd[0][2] * g0.z));
+      Txy = fma2(sp2(st.w[b][1]), txy, Txy);
+      Tz = fmaf(st.w[b][1], tz, Tz);
+      Uyxy = fma2(sp2(wd[b][1]), txy, Uyxy);
+      Uyz = fmaf(wd[b][1], tz, Uyz);
+      Uzxy = fma2(sp2(st.w[b][1]), uxy, Uzxy);
+      Uzz = fmaf(st.w[b][1], uz, Uzz);
+      if (flip) {
+        const float4 *ro = vold + node0 + (a * n1 + b) * n1;
+        const float4 o0 = __ldg(ro), o1 = __ldg(ro + 1), o2 = __ldg(ro + 2);
+        f2 pxy = mul2(sp2(st.w[0][2]), mk2(o0.x, o0.y));
+        pxy = fma2(sp2(st.w[1][2]), mk2(o1.x, o1.y), pxy);
+        pxy = fma2(sp2(st.w[2][2]), mk2(o2.x, o2.y), pxy);
+        const float pz = fmaf(st.w[2][2], o2.z, fmaf(st.w[1][2], o1.z, st.w[0][2] * o0.z));
+        Oxy = fma2(sp2(st.w[b][1]), pxy, Oxy);
+        Oz = fmaf(st.w[b][1], pz, Oz);
+      }
+    }
+    vxy = fma2(sp2(st.w[a][0]), Txy, vxy);
+    vz = fmaf(st.w[a][0], Tz, vz);
+    c0xy = fma2(sp2(wd[a][0]), Txy, c0xy);
+    c0z = fmaf(wd[a][0], Tz, c0z);
+    c1xy = fma2(sp2(st.w[a][0]), Uyxy, c1xy);
+    c1z = fmaf(st.w[a][0], Uyz, c1z);
+    c2xy = fma2(sp2(st.w[a][0]), Uzxy, c2xy);
+    c2z = fmaf(st.w[a][0], Uzz, c2z);
+    if (flip) {
+      oxy = fma2(sp2(st.w[a][0]), Oxy, oxy);
+      oz = fmaf(st.w[a][0], Oz, oz);
+    }
+  }
+  v[0] = vxy.x; v[1] = vxy.y; v[2] = vz;
+  C.d[0][0] = c0xy.x; C.d[0][1] = c0xy.y; C.d[0][2] = c0z;
+  C.d[1][0] = c1xy.x; C.d[1][1] = c1xy.y; C.d[1][2] = c1z;
+  C.d[2][0] = c2xy.x; C.d[2][1] = c2xy.y; C.d[2][2] = c2z;
+  if (flip) {
+    dv[0] = vxy.x - oxy.x; dv[1] = vxy.y - oxy.y; dv[2] = vz - oz;
+  }
+}
+
+}  // namespace mpm

@@ -11,6 +11,7 @@
 // SoA streams, the per-bin shared-memory cell sort, register accumulation, vector REDs, emigrant packing.
 #include "mpm_kernels.cuh"
 #include "mpm_math2.cuh"
+#include "mpm_gather3.cuh"
 
 namespace mpm {
 
@@ -249,78 +250,6 @@ __device__ __forceinline__ bool g2p_one(const Params &P, float dt, const SoA<D> 
   return true;
 }
 
-// Fast 3D gather (:147-156 lifted to 27 nodes) in separable form, (x,y) components as packed pairs:
-//   t_ab = sum_c wz_c g_abc, u_ab = sum_c (wz_c dz_c) g_abc;   T_a = sum_b wy_b t_ab, Uy_a = sum_b (wy_b dy_b) t_ab,
-//   Uz_a = sum_b wy_b u_ab;   v += wx_a T_a, C.col0 += (wx_a dx_a) T_a, C.col1 += wx_a Uy_a, C.col2 += wx_a Uz_a
-// ~190 instructions instead of ~680 for the node-by-node form; fused multiply-adds, algebraically identical
-// (~1e-7 relative from the reference association; MPM_FLAG_STRICT / MPM_FLAG_NAIVE keep g2p_accumulate).
-// C comes back without the constant 4*inv_dx; with FLIP, dv = v - sum w vold.
-__device__ __forceinline__ void gather3_fast(const Params &P, const Stencil<3> &st, const float4 *__restrict__ grid,
-                                             const float4 *__restrict__ vold, bool flip, float *v, Mat<3> &C, float *dv) {
-  float wd[3][3];  // w * (k - fx) per axis
-#pragma unroll
-  for (int k = 0; k < 3; k++)
-#pragma unroll
-    for (int ax = 0; ax < 3; ax++) wd[k][ax] = st.w[k][ax] * ((float)k - st.fx[ax]);
-  f2 vxy = sp2(0.0f), c0xy = sp2(0.0f), c1xy = sp2(0.0f), c2xy = sp2(0.0f), oxy = sp2(0.0f);
-  float vz = 0.0f, c0z = 0.0f, c1z = 0.0f, c2z = 0.0f, oz = 0.0f;
-  const long long n1 = P.n1;
-  const long long node0 = ((long long)(st.base[0] - P.slab_lo) * n1 + st.base[1]) * n1 + st.base[2];
-#pragma unroll
-  for (int a = 0; a < 3; a++) {
-    f2 Txy = sp2(0.0f), Uyxy = sp2(0.0f), Uzxy = sp2(0.0f), Oxy = sp2(0.0f);
-    float Tz = 0.0f, Uyz = 0.0f, Uzz = 0.0f, Oz = 0.0f;
-#pragma unroll
-    for (int b = 0; b < 3; b++) {
-      const float4 *row = grid + node0 + (a * n1 + b) * n1;
-      const float4 g0 = __ldg(row), g1 = __ldg(row + 1), g2 = __ldg(row + 2);
-      f2 txy = mul2(sp2(st.w[0][2]), mk2(g0.x, g0.y));
-      txy = fma2(sp2(st.w[1][2]), mk2(g1.x, g1.y), txy);
-      txy = fma2(sp2(st.w[2][2]), mk2(g2.x, g2.y), txy);
-      const float tz = fmaf(st.w[2][2], g2.z, fmaf(st.w[1][2], g1.z, st.w[0][2] * g0.z));
-      f2 uxy = mul2(sp2(wd[0][2]), mk2(g0.x, g0.y));
-      uxy = fma2(sp2(wd[1][2]), mk2(g1.x, g1.y), uxy);
-      uxy = fma2(sp2(wd[2][2]), mk2(g2.x, g2.y), uxy);
-      const float uz = fmaf(wd[2][2], g2.z, fmaf(wd[1][2], g1.z, wd[0][2] * g0.z));
-      Txy = fma2(sp2(st.w[b][1]), txy, Txy);
-      Tz = fmaf(st.w[b][1], tz, Tz);
-      Uyxy = fma2(sp2(wd[b][1]), txy, Uyxy);
-      Uyz = fmaf(wd[b][1], tz, Uyz);
-      Uzxy = fma2(sp2(st.w[b][1]), uxy, Uzxy);
-      Uzz = fmaf(st.w[b][1], uz, Uzz);
-      if (flip) {
-        const float4 *ro = vold + node0 + (a * n1 + b) * n1;
-        const float4 o0 = __ldg(ro), o1 = __ldg(ro + 1), o2 = __ldg(ro + 2);
-        f2 pxy = mul2(sp2(st.w[0][2]), mk2(o0.x, o0.y));
-        pxy = fma2(sp2(st.w[1][2]), mk2(o1.x, o1.y), pxy);
-        pxy = fma2(sp2(st.w[2][2]), mk2(o2.x, o2.y), pxy);
-        const float pz = fmaf(st.w[2][2], o2.z, fmaf(st.w[1][2], o1.z, st.w[0][2] * o0.z));
-        Oxy = fma2(sp2(st.w[b][1]), pxy, Oxy);
-        Oz = fmaf(st.w[b][1], pz, Oz);
-      }
-    }
-    vxy = fma2(sp2(st.w[a][0]), Txy, vxy);
-    vz = fmaf(st.w[a][0], Tz, vz);
-    c0xy = fma2(sp2(wd[a][0]), Txy, c0xy);
-    c0z = fmaf(wd[a][0], Tz, c0z);
-    c1xy = fma2(sp2(st.w[a][0]), Uyxy, c1xy);
-    c1z = fmaf(st.w[a][0], Uyz, c1z);
-    c2xy = fma2(sp2(st.w[a][0]), Uzxy, c2xy);
-    c2z = fmaf(st.w[a][0], Uzz, c2z);
-    if (flip) {
-      oxy = fma2(sp2(st.w[a][0]), Oxy, oxy);
-      oz = fmaf(st.w[a][0], Oz, oz);
-    }
-  }
-  v[0] = vxy.x; v[1] = vxy.y; v[2] = vz;
-  C.d[0][0] = c0xy.x; C.d[0][1] = c0xy.y; C.d[0][2] = c0z;
-  C.d[1][0] = c1xy.x; C.d[1][1] = c1xy.y; C.d[1][2] = c1z;
-  C.d[2][0] = c2xy.x; C.d[2][1] = c2xy.y; C.d[2][2] = c2z;
-  if (flip) {
-    dv[0] = vxy.x - oxy.x; dv[1] = vxy.y - oxy.y; dv[2] = vz - oz;
-  }
-}
-
 // nodes straight from global memory through the read-only path
 template <int D>
 struct GlobalFetch {
@@ -440,7 +369,11 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
                 const void *__restrict__ vold_in, float dt_g2p, MigPtrs mig) {
   constexpr int M = 1, L = B + 2 * M;
   constexpr int NC = D == 2 ? L * L : L * L * L;
-  __shared__ CellRec<D> rec[CAP];
+  // records as float4 PLANES (a | b [| c | d]): lane i of a warp writes 16 bytes at 16*i -- conflict-free -- and the
+  // phase-2 reads of a dozen scattered records spread over 8 bank groups instead of 2 (the 64-byte AoS records cost
+  // 16 wavefronts per LDS.128: the 3D kernel ran at 77 % of the L1 data-pipe peak, profiles/r02_ncu_full_c5.md)
+  constexpr int NPL = D == 2 ? 2 : 4;
+  __shared__ float4 recp[NPL * CAP];
   __shared__ unsigned short cell_of[CAP], rank_of[CAP], sorted[CAP];
   __shared__ int cnt[NC + 1];
   // phase-2 work items: (cell, first record, record count); a cell with more than RM records is
@@ -448,6 +381,7 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
   constexpr int RM = 8, MAXI = NC + CAP / RM + 1;
   __shared__ int item_first[NC + 1];              // per cell: index of its first item (exclusive scan)
   __shared__ unsigned short item_cell[MAXI];
+  __shared__ int wsum[4];
   const int tid = threadIdx.x;
   const int bin = G.active ? G.active[blockIdx.x] : (int)blockIdx.x;
   const int s0 = bin_start[bin], s1 = bin_start[bin + 1];
@@ -519,7 +453,26 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
         int r = atomicAdd(&cnt[cell], 1);
         cell_of[i] = (unsigned short)cell;
         rank_of[i] = (unsigned short)r;
-        pack_rec<D>(rec[i], st.fx, mv, affine);
+        if constexpr (FAST && D == 3) {
+          // phase 2 works on the separable form w_abc * (q + a cs_0 + b cs_1 + c cs_2) (see there): form cs_k = affine
+          // column k * dx and q = m v - sum_k fx_k cs_k ONCE here instead of in each of the item's three threads
+#pragma unroll
+          for (int k = 0; k < D; k++)
+#pragma unroll
+            for (int r = 0; r < D; r++) affine.d[k][r] = affine.d[k][r] * P.dx;
+#pragma unroll
+          for (int k = 0; k < D; k++)
+#pragma unroll
+            for (int r = 0; r < D; r++) mv[r] = __fmaf_rn(-st.fx[k], affine.d[k][r], mv[r]);
+        }
+        CellRec<D> rr;
+        pack_rec<D>(rr, st.fx, mv, affine);
+        recp[i] = rr.a;
+        recp[CAP + i] = rr.b;
+        if constexpr (D == 3) {
+          recp[2 * CAP + i] = rr.c;
+          recp[3 * CAP + i] = rr.d;
+        }
       } else {  // drifted past the margin since the last re-sort: plain per-particle scatter
         cell_of[i] = 0xffffu;
         n_fallback++;
@@ -536,28 +489,40 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
       }
     }
     __syncthreads();
-    // ---- exclusive scans (NC <= 216) by warp 0, 32 cells per round: record starts and item starts ----
-    if (tid < 32) {
-      int run = 0, irun = 0;
-      for (int k0 = 0; k0 < NC; k0 += 32) {
-        int k = k0 + tid;
-        int v = k < NC ? cnt[k] : 0;
-        int iv = (v + RM - 1) / RM;  // items of this cell
-        int inc = v, iinc = iv;
+    // ---- exclusive scans over the NC <= 2*NT cells on ALL warps (two cells per thread, count | items packed in one
+    // word: both totals stay below 2^16): record starts and item starts.  (Round 1 scanned on warp 0 in 7 rounds
+    // while the other warps waited at the barrier.) ----
+    {
+      static_assert(NC <= 2 * NT && NT == 128, "two cells per thread, four warps");
+      const int lane = tid & 31, wid = tid >> 5;
+      const int k0 = 2 * tid, k1 = 2 * tid + 1;
+      const int v0 = k0 < NC ? cnt[k0] : 0, v1 = k1 < NC ? cnt[k1] : 0;
+      const int p0 = v0 | (((v0 + RM - 1) / RM) << 16), p1 = v1 | (((v1 + RM - 1) / RM) << 16);
+      int inc = p0 + p1;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          int t = __shfl_up_sync(0xffffffffu, inc, d);
-          int u = __shfl_up_sync(0xffffffffu, iinc, d);
-          if (tid >= d) { inc += t; iinc += u; }
-        }
-        if (k < NC) {
-          cnt[k] = run + inc - v;
-          item_first[k] = irun + iinc - iv;
-        }
-        run += __shfl_sync(0xffffffffu, inc, 31);
-        irun += __shfl_sync(0xffffffffu, iinc, 31);
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
       }
-      if (tid == 0) { cnt[NC] = run; item_first[NC] = irun; }
+      if (lane == 31) wsum[wid] = inc;
+      __syncthreads();  // also: every cnt[] has been read before any is overwritten
+      int pre = 0;
+#pragma unroll
+      for (int w = 0; w < 3; w++)
+        if (w < wid) pre += wsum[w];
+      const int ex = pre + inc - (p0 + p1);
+      if (k0 < NC) {
+        cnt[k0] = ex & 0xffff;
+        item_first[k0] = ex >> 16;
+      }
+      if (k1 < NC) {
+        cnt[k1] = (ex + p0) & 0xffff;
+        item_first[k1] = (ex + p0) >> 16;
+      }
+      if (tid == NT - 1) {
+        cnt[NC] = (pre + inc) & 0xffff;
+        item_first[NC] = (pre + inc) >> 16;
+      }
     }
     __syncthreads();
     for (int k = tid; k < NC; k += NT)
@@ -599,7 +564,16 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
         Stencil<D> st;
         float mv[D];
         Mat<D> affine;
-        unpack_rec<D>(rec[i], st.fx, mv, affine);
+        {
+          CellRec<D> rr;
+          rr.a = recp[i];
+          rr.b = recp[CAP + i];
+          if constexpr (D == 3) {
+            rr.c = recp[2 * CAP + i];
+            rr.d = recp[3 * CAP + i];
+          }
+          unpack_rec<D>(rr, st.fx, mv, affine);
+        }
 #pragma unroll
         for (int k = 0; k < D; k++) {  // the same three expressions as make_stencil (:61-63)
           st.w[0][k] = 0.5f * ((1.5f - st.fx[k]) * (1.5f - st.fx[k]));
@@ -610,19 +584,14 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
           // 3D: the separable form below on packed pairs.  A node value is the 4-vector (m v + A dpos, m); with
           // Q = (q, mass_p) and CS_k = (affine column k * dx, 0) it is w_abc * (Q + a CS_0 + b CS_1 + c CS_2): every
           // step is two FFMA2 (xy | z,m) instead of four scalar operations.
-          const float dxs = P.dx;
+          // (the record already holds cs_k in the affine slots and q in the m*v slots: phase 1)
           f2 cs_xy[3], cs_zm[3];
 #pragma unroll
           for (int k = 0; k < 3; k++) {
-            cs_xy[k] = mul2(mk2(affine.d[k][0], affine.d[k][1]), sp2(dxs));
-            cs_zm[k] = mk2(affine.d[k][2] * dxs, 0.0f);
+            cs_xy[k] = mk2(affine.d[k][0], affine.d[k][1]);
+            cs_zm[k] = mk2(affine.d[k][2], 0.0f);
           }
-          f2 q_xy = mk2(mv[0], mv[1]), q_zm = mk2(mv[2], P.mass_p);
-#pragma unroll
-          for (int k = 0; k < 3; k++) {
-            q_xy = fma2(sp2(-st.fx[k]), cs_xy[k], q_xy);
-            q_zm = fma2(sp2(-st.fx[k]), cs_zm[k], q_zm);
-          }
+          const f2 q_xy = mk2(mv[0], mv[1]), q_zm = mk2(mv[2], P.mass_p);
           const int a = a_lo;  // TPC == 3: this thread's stencil row
           const float wa = a == 0 ? st.w[0][0] : (a == 1 ? st.w[1][0] : st.w[2][0]);
           const f2 xa_xy = fma2(sp2((float)a), cs_xy[0], q_xy), xa_zm = fma2(sp2((float)a), cs_zm[0], q_zm);

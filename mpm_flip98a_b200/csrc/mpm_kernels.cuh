@@ -86,6 +86,25 @@ struct Substep2dArgs {
 void launch_substep2d(const Substep2dArgs &a, bool flip, bool mig, bool resort, cudaStream_t st);
 int substep2d_chunk_capacity();  // particles per work-list entry (the kernel's shared-memory chunk)
 
+// ---- the 3D default G2P kernel (mpm_substep3d.cu): early stores, optional on-the-fly re-sort ----
+struct G2p3Args {
+  Params P;
+  float dt;
+  SoA<3> s;                   // particle storage (updated in place unless RESORT)
+  SoA<3> d;                   // RESORT: the other storage buffer
+  long long first, n;         // storage slots [first, n)
+  const float4 *grid;         // updated grid of this substep
+  const float4 *vold;         // FLIP: pre-gravity node velocity
+  const int *new_start;       // RESORT: cell starts of the new order
+  const unsigned *key;        // RESORT: new cell of slot i (k_count_rank, positions before this substep)
+  const unsigned *rank;       // RESORT: rank of slot i inside its new cell
+  MigPtrs mig;
+  int *status;
+  unsigned long long *stats;
+  const int *dev_n;           // x-slab handles: exact storage extent on the device
+};
+void launch_g2p3(const G2p3Args &a, bool flip, bool mig, bool resort, cudaStream_t st);
+
 // ---- MPM_FLAG_DETERMINISTIC (mpm_deterministic.cu): fixed-order P2G without atomics ----
 template <int D>
 void launch_det_cell_keys(const Params &P, const SoA<D> &s, long long n, unsigned *key, int *status, cudaStream_t st);
