@@ -245,6 +245,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N > 1: weak (per-GPU work of N=1, default) or strong (the N=1 problem cut into N slabs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-rebalance", action="store_true",
+                    help="N > 1: keep the equal-particle-count slabs (default: move the cuts to equalise measured cost)")
     ap.add_argument("--rebin-every", type=int, default=0, help="storage re-sort interval (0 = engine default)")
     args = ap.parse_args()
     if args.warm_substeps is None:
@@ -508,10 +510,38 @@ def slab_plan(args, world):
     return descr, dim, n_grid, alpha, slabs, generate
 
 
+def rebalanced_cuts(slabs, costs, n_grid, edge, x_range):
+    """New slab cuts that equalise the MEASURED per-rank cost, assuming each rank's cost is spread evenly over the filled
+    columns it owns (piecewise-constant cost density along x)."""
+    world = len(slabs)
+    lo_f, hi_f = x_range[0] * n_grid, x_range[1] * n_grid
+    segs = []
+    for (lo, hi), t in zip(slabs, costs):
+        a, b = max(lo, lo_f), min(hi, hi_f)
+        segs.append((a, b, t / max(b - a, 1e-9)))
+    total = float(sum(costs))
+    cuts = [0]
+    for r in range(1, world):
+        target, acc, x = total * r / world, 0.0, segs[-1][1]
+        for a, b, d in segs:
+            c = d * (b - a)
+            if acc + c >= target:
+                x = a + (target - acc) / d
+                break
+            acc += c
+        cut = int(round(x / edge)) * edge
+        cuts.append(min(max(cut, cuts[-1] + edge), n_grid - edge * (world - r)))
+    cuts.append(n_grid)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
 def run_slabs(args, rank, world, local):
     """N > 1: one x-slab per rank (mpm_flip98a_b200/parallel.py): ONE fixed-size NCCL P2P message per neighbour and
     substep (ghost-column sums + emigrants), no host synchronisation; by default the interior bins run on a side
-    stream while the boundary is exchanged (MPM_FLAG_OVERLAP)."""
+    stream while the boundary is exchanged (MPM_FLAG_OVERLAP).  The slabs start as equal particle counts; a short
+    calibration run measures each rank's device time per substep and, when they differ by more than 4 %, the cuts are
+    moved to equalise the measured cost (the material bands of c4 / c5 lie along x and cost differently) and the
+    ranks regenerate their particles -- all before anything is timed."""
     import torch
     import torch.distributed as dist
     import mpm_flip98a_b200 as mpm
@@ -521,51 +551,83 @@ def run_slabs(args, rank, world, local):
         raise SystemExit("multi-GPU bench: workloads c4 (default), c5, c3")
     descr, dim, n_grid, alpha, slabs, generate = slab_plan(args, world)
     words = 14 if dim == 2 else 26
+    edge = 8 if dim == 2 else 4
+    x_range = (0.05, 0.95) if args.workload in ("c4", "c5") else (0.05, 0.52)
     dt, vol = scenes.scaled_constants(n_grid, dim)
-    lo, hi = slabs[rank]
     dev = "cuda:%d" % local
-    # this rank's particles: generate the cell columns that can hold owned base cells, keep the owned
-    # (generated straight into the pinned upload buffer and compacted in place, chunk by chunk: no second copy)
-    if args.workload == "c4":
-        n_max = scenes.slab_fill_2d_count(n_grid, columns=(lo, hi + 1))
-        host = torch.empty((n_max, words), dtype=torch.float32, pin_memory=True)
-        rec = generate(lo, hi + 1, out=host.numpy())
-    else:
-        rec = generate(lo, hi + 1)
-        host = torch.empty((len(rec), words), dtype=torch.float32, pin_memory=True)
-        host.numpy()[:] = rec
-        rec = host.numpy()[:len(rec)]
-    n_local = 0
-    for c0 in range(0, len(rec), 1 << 22):
-        blk = rec[c0:c0 + (1 << 22)]
-        b = parallel.base_column(blk[:, 0], n_grid)
-        kept = blk[(b >= lo) & (b < hi)]
-        host.numpy()[n_local:n_local + len(kept)] = kept
-        n_local += len(kept)
-    del rec
-    counts = torch.zeros(world, dtype=torch.int64, device=dev)
-    counts[rank] = n_local
-    dist.all_reduce(counts)
-    n_total = int(counts.sum())
-    first_id = int(counts[:rank].sum())
-    assert n_total < 2 ** 31, "int32 particle ids"
-    ids = torch.arange(first_id, first_id + n_local, dtype=torch.int32).pin_memory()
-    cap = int(n_local * 1.1) + 65536
-    ids_out = torch.empty(cap, dtype=torch.int32).pin_memory()
-    host_out = torch.empty((cap, words), dtype=torch.float32, pin_memory=True)  # e2e read-back (storage order)
-
     overlap = dim == 2 and not args.no_overlap and not args.naive and not args.no_fuse
     # with the overlapped schedule the engine's interior launch runs on a lowest-priority side stream; the main stream
     # (boundary bins, exchange helpers) and NCCL's own stream (TORCH_NCCL_HIGH_PRIORITY, set in __main__) outrank it
     stream = torch.cuda.Stream(priority=-1) if overlap else torch.cuda.Stream()
     flags = FLAG_NAIVE if args.naive else ((FLAG_OVERLAP if overlap else 0) | (16 if args.no_fuse else 0))
-    with torch.cuda.stream(stream):
+    PH = ("clear", "p2g", "grid", "g2p", "bin", "halo", "migrate")
+
+    def setup(slabs):
+        """this rank's particles for `slabs` (generated straight into a pinned upload buffer and compacted in place,
+        chunk by chunk: no second copy), an engine handle, the exchange object"""
+        lo, hi = slabs[rank]
+        if args.workload == "c4":
+            n_max = scenes.slab_fill_2d_count(n_grid, columns=(lo, hi + 1))
+            host = torch.empty((n_max, words), dtype=torch.float32, pin_memory=True)
+            rec = generate(lo, hi + 1, out=host.numpy())
+        else:
+            rec = generate(lo, hi + 1)
+            host = torch.empty((len(rec), words), dtype=torch.float32, pin_memory=True)
+            host.numpy()[:] = rec
+            rec = host.numpy()[:len(rec)]
+        n_local = 0
+        for c0 in range(0, len(rec), 1 << 22):
+            blk = rec[c0:c0 + (1 << 22)]
+            b = parallel.base_column(blk[:, 0], n_grid)
+            kept = blk[(b >= lo) & (b < hi)]
+            host.numpy()[n_local:n_local + len(kept)] = kept
+            n_local += len(kept)
+        del rec
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        counts[rank] = n_local
+        dist.all_reduce(counts)
+        n_total = int(counts.sum())
+        first_id = int(counts[:rank].sum())
+        assert n_total < 2 ** 31, "int32 particle ids"
+        ids = torch.arange(first_id, first_id + n_local, dtype=torch.int32).pin_memory()
+        cap = int(n_local * 1.1) + 65536
         eng = mpm.Engine(dim=dim, n_grid=n_grid, capacity=cap, dt=dt, vol_p=vol, alpha=alpha, device=local,
                          flags=flags, stream=stream.cuda_stream, rebin_every=args.rebin_every, slab=(lo, hi))
         up = lambda: eng._check(eng.lib.mpm_upload_particles_ids(eng.h, host.data_ptr(), ids.data_ptr(), n_local, 0))
         up()
         r = parallel.SlabRank(eng, rank, world, dev)
         ex = parallel.DistExchange(r, shared_stream=True)  # engine and NCCL ops are ordered on `stream`
+        return host, ids, n_local, n_total, cap, eng, up, r, ex
+
+    with torch.cuda.stream(stream):
+        balance = {"passes": 0, "cost_ms_per_rank": None, "imbalance_max_over_mean": None}
+        for attempt in range(3):
+            host, ids, n_local, n_total, cap, eng, up, r, ex = setup(slabs)
+            # calibration: each rank's device time per substep on a short warm window
+            parallel.step_dist(r, ex, min(200, max(20, args.warm_substeps // 8)), settle=False)
+            eng.profile_enable(True)
+            parallel.step_dist(r, ex, 24, settle=False)
+            prof = eng.profile()
+            eng.profile_enable(False)
+            mine = sum(prof[k][0] for k in PH) / 24.0
+            costs = torch.zeros(world, dtype=torch.float64, device=dev)
+            costs[rank] = mine
+            dist.all_reduce(costs)
+            costs = [float(c) for c in costs]
+            imb = max(costs) / (sum(costs) / world)
+            balance.update(cost_ms_per_rank=[round(c, 4) for c in costs], imbalance_max_over_mean=round(imb, 4))
+            if imb <= 1.04 or attempt == 2 or args.no_rebalance:
+                break
+            new = rebalanced_cuts(slabs, costs, n_grid, edge, x_range)
+            if new == slabs:
+                break
+            eng.close()
+            del host, ids, eng, up, r, ex
+            slabs = new
+            balance["passes"] += 1
+        lo, hi = slabs[rank]
+        ids_out = torch.empty(cap, dtype=torch.int32).pin_memory()
+        host_out = torch.empty((cap, words), dtype=torch.float32, pin_memory=True)  # e2e read-back (storage order)
         parallel.step_dist(r, ex, args.warm_substeps, settle=False)
         if eng.poll_status() != 0:
             raise SystemExit("rank %d: engine status after warm-up: %s" % (rank, eng.lib.mpm_last_error(eng.h)))
@@ -612,8 +674,14 @@ def run_slabs(args, rank, world, local):
         value = n_total * args.steps / (ms * 1e-3)
         prof["timed_interval"] = timed_interval
         # device time of this rank's phases vs the wall of the step: what the exchange costs on top of the compute
-        phase_sum = sum(prof[k][0] for k in ("clear", "p2g", "grid", "g2p", "bin", "halo", "migrate")) / args.steps
+        phase_sum = sum(prof[k][0] for k in PH) / args.steps
         prof["exchange_bubble_ms_per_step"] = ms / args.steps - phase_sum
+        ph_all = torch.zeros(world, dtype=torch.float64, device=dev)
+        ph_all[rank] = phase_sum
+        dist.all_reduce(ph_all)
+        n_all = torch.zeros(world, dtype=torch.int64, device=dev)
+        n_all[rank] = n_local
+        dist.all_reduce(n_all)
 
         # ---- e2e: every rank uploads its host buffer, FRAME substeps, reads its particles back -------
         def e2e_call():
@@ -638,8 +706,14 @@ def run_slabs(args, rank, world, local):
     if rank == 0:
         line = make_line(args, world, n_total, n_local, words, dim, n_grid, alpha, dt, descr, ms, value, e2e_value, prof,
                          clocks, scaling=args.scaling,
-                         extra_config={"decomposition": "x-slabs cut for equal particle counts, %d..%d columns per GPU"
-                                                        % (min(b - a for a, b in slabs), max(b - a for a, b in slabs)),
+                         extra_config={"decomposition": "x-slabs of %d..%d columns per GPU: cut for equal particle counts, "
+                                                        "then moved to equalise the device time per substep each rank "
+                                                        "measured in a calibration run (%d rebalancing pass%s)"
+                                                        % (min(b - a for a, b in slabs), max(b - a for a, b in slabs),
+                                                           balance["passes"], "" if balance["passes"] == 1 else "es"),
+                                       "slabs": slabs, "particles_per_rank": [int(x) for x in n_all],
+                                       "calibration": balance,
+                                       "phase_ms_per_substep_per_rank": [round(float(x), 4) for x in ph_all],
                                        "scaling_rule": ("weak: n_grid = %d (N=1: %d), same fill fractions -> particles and "
                                                         "nodes per GPU as at N=1" % (n_grid, WORKLOADS[args.workload][2]))
                                        if args.scaling == "weak" else "strong: the N=1 problem cut into N slabs",

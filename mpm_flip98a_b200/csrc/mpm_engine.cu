@@ -190,6 +190,7 @@ struct mpm_handle {
       if (h->spans.size() >= 8192) {
         h->join_side();
         cudaStreamSynchronize(h->stream);
+        if (st != h->stream) cudaStreamSynchronize(st);  // a side-stream span: its closing event was recorded just now
         h->flush_spans();
       }
     }
@@ -227,7 +228,10 @@ struct mpm_handle {
   bool fast3d() const {
     return binned && D == 3 && !fused && !(cfg.flags & (MPM_FLAG_STRICT | MPM_FLAG_G2P_TILE));
   }
-  bool resorts_on_the_fly() const { return fast2d() || fast3d(); }
+  // 3D default: G2P and the next P2G in ONE kernel (k_substep3d); MPM_FLAG_NO_FUSE keeps the two kernels above
+  bool fast3f() const { return fused && D == 3; }
+  bool resorts_on_the_fly() const { return fast2d() || fast3d() || fast3f(); }
+  int chunk_capacity() const { return D == 2 ? substep2d_chunk_capacity() : substep3d_chunk_capacity(); }
   void carve(int b);
   int substep(float dt, int n_steps);
   int step_p2g(float dt);
@@ -420,13 +424,18 @@ int mpm_handle::init() {
       return rc;
   }
   // 2D only: in 3D the Jacobi-SVD-heavy kernels are compute-bound and fusing them costs occupancy (measured slower)
-#ifndef MPM_FUSE_3D
-#define MPM_FUSE_3D 0
-#endif
-  fused = binned && (D == 2 || MPM_FUSE_3D) && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE));
+  // fused G2P->P2G: 2D k_substep2d (MPM_FLAG_STRICT: the generic k_p2g_cells<FUSED>), 3D k_substep3d (3D + STRICT stays
+  // unfused: the exact-association generic kernel spills when fused)
+  fused = binned && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE)) && (D == 2 || !(cfg.flags & MPM_FLAG_STRICT));
   pipelined = fused || multi;
   if (pipelined)
     if ((rc = dalloc(&grid_next, (size_t)nodes))) return rc;
+  if (fast3f()) {  // work list of the fused 3D kernel
+    chunks_cap = (long long)G.n_bins + cap / chunk_capacity() + 2;
+    for (int b = 0; b < 2; b++)
+      if ((rc = dalloc(&chunks_buf[b], (size_t)chunks_cap))) return rc;
+    if ((rc = dalloc(&chunk_offs, (size_t)G.n_bins + 4))) return rc;
+  }
   if (fast2d()) {
     tiles_x = (P.ncol + 7) / 8;
     tiles_y = (P.n1 + 7) / 8;
@@ -559,7 +568,8 @@ int mpm_handle::begin_resort() {
   MPM_CUDA(cudaMemcpyAsync(&resort_host[0], active_offs + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
   MPM_CUDA(cudaMemcpyAsync(&resort_host[1], ns + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
   if (chunk_offs) {
-    launch_active_chunks(ns, G.n_bins, G.nb[1], substep2d_chunk_capacity(), chunk_offs, sb.scan_tmp, chunks_buf[bs ^ 1], stream);
+    launch_active_chunks(ns, G.n_bins, G.nb[1], chunk_capacity(), chunk_offs, sb.scan_tmp, chunks_buf[bs ^ 1], stream,
+                         D == 3 ? G.nb[2] : 0);
     MPM_CUDA(cudaMemcpyAsync(&resort_host[4], chunk_offs + G.n_bins, 4, cudaMemcpyDeviceToHost, stream));
   }
   if (overlap) {
@@ -787,8 +797,8 @@ int mpm_handle::step_grid_g2p(float dt) {
     // 2D default: the packed-math kernel of mpm_substep2d.cu; MPM_FLAG_STRICT (and 3D, if ever fused) keeps
     // k_p2g_cells<FUSED>.  A due re-sort rides on the fast kernel (RESORT variant): first half here, the kernel
     // is the consumer, second half after it has been enqueued.
-    const bool fast = fast2d();
-    const bool resort = fast && resort_due && n > 0;
+    const bool fast = fast2d(), fast3 = fast3f();
+    const bool resort = (fast || fast3) && resort_due && n > 0;
     if (resort) {
       fused_resort_now = true;
       int rc = rebin_storage();
@@ -818,10 +828,37 @@ int mpm_handle::step_grid_g2p(float dt) {
       sa.stats = stats_dev;
       sa.mig = mig;
     }
+    Substep3dArgs sa3;
+    if (fast3) {
+      sa3.P = P;
+      sa3.dt_g2p = dt;
+      sa3.dt_p2g = dt;
+      sa3.s = s3[cur];
+      sa3.d = s3[cur ^ 1];
+      sa3.chunks = chunks_buf[bs];
+      sa3.n_chunks = n_chunks;
+      sa3.new_start = cell_start;
+      sa3.key = sb.key[0];
+      sa3.rank = (const unsigned *)sb.val[0];
+      sa3.grid_in = grid;
+      sa3.vold_in = (const float4 *)vold;
+      sa3.grid_out = grid_next;
+      sa3.status = status_dev;
+      sa3.stats = stats_dev;
+      sa3.mig = mig;
+    }
     const bool flip = P.alpha != 0.0f;
     // part: 0 = everything, 1 = boundary-lo, 2 = interior, 3 = boundary-hi (overlapped schedule)
     auto run_bins = [&](const BinGeom &Gx, MigPtrs mg, cudaStream_t st, int part) {
-      if (fast) {
+      if (fast3) {
+        Substep3dArgs x = sa3;
+        x.mig = mg;
+        const int c0 = part == 0 || part == 1 ? 0 : (part == 2 ? chunk_lo_end : chunk_hi_begin);
+        const int c1 = part == 0 || part == 3 ? n_chunks : (part == 1 ? chunk_lo_end : chunk_hi_begin);
+        x.chunks = sa3.chunks + c0;
+        x.n_chunks = c1 - c0;
+        launch_substep3d(x, flip, mg.enabled != 0, resort, st);
+      } else if (fast) {
         Substep2dArgs x = sa;
         x.G = Gx;
         x.mig = mg;
@@ -853,9 +890,12 @@ int mpm_handle::step_grid_g2p(float dt) {
         GridPtrs<3> gn = gp<3>();
         gn.g = grid_next;
         launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gn, status_dev, stream, dev_ext);
+        if (resort)
+          launch_reorder_scatter<3>(s3[cur], s3[cur ^ 1], n_binned, n, (int)n_cells(), cell_start, sb.key[0],
+                                    (const unsigned *)sb.val[0], stream, dev_ext);
       }
     };
-    if (overlap && act_hi_begin > act_lo_end && D == 2) {
+    if (overlap && act_hi_begin > act_lo_end && (fast || fast3)) {
       MPM_CUDA(cudaEventRecord(ev_ready, stream));  // grid updated, next grid cleared, (re-sort tables ready)
       {
         // boundary bins (both sides) FIRST and on the main stream: their emigrants and shared columns are what

@@ -379,7 +379,8 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
   // phase-2 work items: (cell, first record, record count); a cell with more than RM records is
   // split evenly so that the lanes of a warp walk runs of similar length
   constexpr int RM = 8, MAXI = NC + CAP / RM + 1;
-  __shared__ int item_first[NC + 1];              // per cell: index of its first item (exclusive scan)
+  __shared__ unsigned short item_first[NC + 1];   // per cell: index of its first item (exclusive scan); 16 bits keep
+                                                  // the 3D kernel at 37.7 KB = SIX resident CTAs per SM instead of five
   __shared__ unsigned short item_cell[MAXI];
   __shared__ int wsum[4];
   const int tid = threadIdx.x;
@@ -513,15 +514,15 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
       const int ex = pre + inc - (p0 + p1);
       if (k0 < NC) {
         cnt[k0] = ex & 0xffff;
-        item_first[k0] = ex >> 16;
+        item_first[k0] = (unsigned short)(ex >> 16);
       }
       if (k1 < NC) {
         cnt[k1] = (ex + p0) & 0xffff;
-        item_first[k1] = (ex + p0) >> 16;
+        item_first[k1] = (unsigned short)((ex + p0) >> 16);
       }
       if (tid == NT - 1) {
         cnt[NC] = (pre + inc) & 0xffff;
-        item_first[NC] = (pre + inc) >> 16;
+        item_first[NC] = (unsigned short)((pre + inc) >> 16);
       }
     }
     __syncthreads();
@@ -721,12 +722,9 @@ template <int D, bool FAST, bool MIG, bool FUSED>
 static void launch_cells_variant(const Params &P, const BinGeom &G, float dt, const SoA<D> &s, const int *bin_start,
                                  float4 *grid, int *status, unsigned long long *stats, const float4 *grid_in,
                                  const void *vold_in, float dt_g2p, MigPtrs mig, cudaStream_t st) {
-#ifndef MPM_FUSE_3D
-#define MPM_FUSE_3D 0
-#endif
-  if constexpr (FUSED && D == 3 && !MPM_FUSE_3D) {
-    // never launched: the engine fuses in 2D only (in 3D the fused kernel loses more to register pressure than
-    // it saves in traffic); not instantiating it keeps 1 KB-stack kernels out of the library
+  if constexpr (FUSED && D == 3) {
+    // never launched: the fused 3D kernel is k_substep3d (mpm_substep3d.cu); this generic one spills ~0.5 KB when
+    // fused in 3D (measured 5.1 vs 3.7 ms), so it is not instantiated
     (void)P; (void)G; (void)dt; (void)s; (void)bin_start; (void)grid; (void)status; (void)stats; (void)grid_in;
     (void)vold_in; (void)dt_g2p; (void)mig; (void)st;
   } else if constexpr (D == 2)

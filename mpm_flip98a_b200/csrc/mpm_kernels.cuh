@@ -105,6 +105,27 @@ struct G2p3Args {
 };
 void launch_g2p3(const G2p3Args &a, bool flip, bool mig, bool resort, cudaStream_t st);
 
+// ---- the fused 3D substep kernel (mpm_substep3d.cu): G2P -> P2G in one pass, optional on-the-fly re-sort ----
+struct Substep3dArgs {
+  Params P;
+  float dt_g2p, dt_p2g;
+  SoA<3> s;                   // particle storage (updated in place unless RESORT)
+  SoA<3> d;                   // RESORT: the other storage buffer
+  const int4 *chunks;         // work list: (bin, first slot, particles, bin x << 20 | bin y << 10 | bin z), one CTA each
+  int n_chunks;
+  const int *new_start;       // RESORT: cell starts of the new order
+  const unsigned *key;        // RESORT: new cell of slot i (k_count_rank, positions before this substep)
+  const unsigned *rank;       // RESORT: rank of slot i inside its new cell
+  const float4 *grid_in;      // updated grid of this substep
+  const float4 *vold_in;      // FLIP: pre-gravity node velocity
+  float4 *grid_out;           // P2G target of the next substep (zeroed)
+  int *status;
+  unsigned long long *stats;
+  MigPtrs mig;
+};
+void launch_substep3d(const Substep3dArgs &a, bool flip, bool mig, bool resort, cudaStream_t st);
+int substep3d_chunk_capacity();
+
 // ---- MPM_FLAG_DETERMINISTIC (mpm_deterministic.cu): fixed-order P2G without atomics ----
 template <int D>
 void launch_det_cell_keys(const Params &P, const SoA<D> &s, long long n, unsigned *key, int *status, cudaStream_t st);
@@ -162,8 +183,9 @@ void launch_iota(int *v, long long n, cudaStream_t st);
 void launch_active_bins(const int *bin_start, int n_bins, unsigned *offs, unsigned *scan_tmp, int *active, cudaStream_t st);
 // chunks[0..count) = (bin, first slot, particles, bin x << 16 | bin y) per chunk of <= cap particles of a non-empty
 // bin, ascending bin; offs = scratch of n_bins+1 u32 (afterwards: chunks before bin b); count -> offs[n_bins]
+// nb_z > 0: 3D bins, the last word is bin x << 20 | bin y << 10 | bin z
 void launch_active_chunks(const int *bin_start, int n_bins, int nb_y, int cap, unsigned *offs, unsigned *scan_tmp,
-                          int4 *chunks, cudaStream_t st);
+                          int4 *chunks, cudaStream_t st, int nb_z = 0);
 // exclusive scan of unsigned data[n] in place (tmp: scan_tmp_elems(n))
 void exclusive_scan_u32(unsigned *data, long long n, unsigned *tmp, cudaStream_t st);
 

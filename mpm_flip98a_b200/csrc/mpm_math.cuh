@@ -290,13 +290,27 @@ MPM_HD Mat<3> rotation_of_svd(const Mat<3> &F) {
   return mat_mul<3>(U, mat_transposed<3>(V));
 }
 
+// Device: reciprocal square root / division by the special-function unit (<= 2 ulp) in the 3D decompositions: the Jacobi rotations of
+// plastic_project3 (a rotation angle that is off by an ulp leaves an off-diagonal of ~1e-7 |apq| behind, far below
+// what the next sweep tests for) and the 0.5 / det of the Newton polar iteration (self-correcting).  Host (tests/host_check.cpp): the oracle's exact statements.
+#if defined(__CUDA_ARCH__)
+#define MPM_RSQRT(x) rsqrtf(x)
+#define MPM_FDIV(a, b) __fdividef((a), (b))
+#define MPM_SQRT_POS(x) ((x) * rsqrtf(x))
+#else
+#define MPM_RSQRT(x) (1.0f / sqrtf(x))
+#define MPM_FDIV(a, b) ((a) / (b))
+#define MPM_SQRT_POS(x) sqrtf(x)
+#endif
 // Rotation factor for the 3D stress (the 3D lift has no counterpart in the reference; the CPU oracle defines it with
 // the very same statements, oracle/mpm_oracle.cpp polar_newton3 / rotation3): Newton's iteration for the polar
 // decomposition, X <- (X + X^-T) / 2 from X0 = F, converges quadratically to the rotation R of F = R S.
-// |X_{k+1} - X_k| <= 2e-4 means X_{k+1} is within ~2e-8 of R (below fp32 rounding): 2-3 iterations for snow (F within
-// 2.5 % of a rotation after the plastic clamp), 3-4 for a jelly under load, ~70 instructions each -- against ~1500 for
+// |X_{k+1} - X_k| <= 4e-4 means X_{k+1} is within ~8e-8 of R (fp32 rounding): 2 iterations for snow (F within
+// 2.5 % of a rotation after the plastic clamp), 3-4 for a jelly under load, ~65 instructions each (cofactors as
+// multiply + FMA) -- against ~1500 for
 // the 4-sweep Jacobi SVD whose U V^T it replaced in round 2 (the two agree to ~1e-6, tests/test_host_math.py).
 // Returns false for a near-singular or inverted F (det <= 1e-6 |F|^3): the callers then take the SVD.
+MPM_HD float cof(float p, float q, float r, float t) { return fmaf(p, q, -(r * t)); }  // p q - r t
 MPM_HD bool polar_newton3(const Mat<3> &F, Mat<3> &X) {
   X = F;
   float scale = 0.0f;
@@ -308,12 +322,12 @@ MPM_HD bool polar_newton3(const Mat<3> &F, Mat<3> &X) {
   for (int it = 0; it < 12; it++) {
     const float *a = X.d[0], *b = X.d[1], *c = X.d[2];
     Mat<3> K;  // cofactors: columns b x c, c x a, a x b  (X^-T = K / det)
-    K.d[0][0] = b[1] * c[2] - b[2] * c[1]; K.d[0][1] = b[2] * c[0] - b[0] * c[2]; K.d[0][2] = b[0] * c[1] - b[1] * c[0];
-    K.d[1][0] = c[1] * a[2] - c[2] * a[1]; K.d[1][1] = c[2] * a[0] - c[0] * a[2]; K.d[1][2] = c[0] * a[1] - c[1] * a[0];
-    K.d[2][0] = a[1] * b[2] - a[2] * b[1]; K.d[2][1] = a[2] * b[0] - a[0] * b[2]; K.d[2][2] = a[0] * b[1] - a[1] * b[0];
-    const float det = a[0] * K.d[0][0] + a[1] * K.d[0][1] + a[2] * K.d[0][2];
+    K.d[0][0] = cof(b[1], c[2], b[2], c[1]); K.d[0][1] = cof(b[2], c[0], b[0], c[2]); K.d[0][2] = cof(b[0], c[1], b[1], c[0]);
+    K.d[1][0] = cof(c[1], a[2], c[2], a[1]); K.d[1][1] = cof(c[2], a[0], c[0], a[2]); K.d[1][2] = cof(c[0], a[1], c[1], a[0]);
+    K.d[2][0] = cof(a[1], b[2], a[2], b[1]); K.d[2][1] = cof(a[2], b[0], a[0], b[2]); K.d[2][2] = cof(a[0], b[1], a[1], b[0]);
+    const float det = fmaf(a[2], K.d[0][2], fmaf(a[1], K.d[0][1], a[0] * K.d[0][0]));
     if (!(det > 1e-6f * scale * scale * scale)) return false;
-    const float h = 0.5f / det;
+    const float h = MPM_FDIV(0.5f, det);
     float delta = 0.0f;
 #pragma unroll
     for (int cc = 0; cc < 3; cc++)
@@ -323,7 +337,7 @@ MPM_HD bool polar_newton3(const Mat<3> &F, Mat<3> &X) {
         delta = fmaxf(delta, fabsf(y - X.d[cc][k]));
         X.d[cc][k] = y;
       }
-    if (delta <= 2e-4f) break;
+    if (delta <= 4e-4f) break;
   }
   return true;
 }
@@ -333,18 +347,6 @@ MPM_HD Mat<3> rotation_of(const Mat<3> &F) {
   return rotation_of_svd(F);
 }
 
-// Device: reciprocal square root / division by the special-function unit (<= 2 ulp) inside the Jacobi rotations of
-// plastic_project3 -- a rotation angle that is off by an ulp leaves an off-diagonal of ~1e-7 |apq| behind, far below
-// what the next sweep tests for.  Host (tests/host_check.cpp): the oracle's exact statements.
-#if defined(__CUDA_ARCH__)
-#define MPM_RSQRT(x) rsqrtf(x)
-#define MPM_FDIV(a, b) __fdividef((a), (b))
-#define MPM_SQRT_POS(x) ((x) * rsqrtf(x))
-#else
-#define MPM_RSQRT(x) (1.0f / sqrtf(x))
-#define MPM_FDIV(a, b) ((a) / (b))
-#define MPM_SQRT_POS(x) sqrtf(x)
-#endif
 MPM_HD float dot3f(const float *a, const float *b) { return fmaf(a[2], b[2], fmaf(a[1], b[1], a[0] * b[0])); }
 
 // One Jacobi rotation of the symmetric 3x3 (diagonal app, aqq; off-diagonal apq; arp, arq = the entries that couple
@@ -470,8 +472,11 @@ MPM_HD int material_index(const Params &P, int c) {
 
 // :67-89 -- the matrix `affine` such that the node contribution is
 //   w * ( (mass_p * v, mass_p) + (affine * dpos, 0) ),  dpos = (node_offset - fx) * dx
+// `rot`: the rotation factor of F (:75-76) when the caller already has it (the fused 3D kernel takes it from the snow
+// projection of the same substep), else nullptr: computed here.  Not read for fluids.
 template <int D>
-MPM_HD Mat<D> p2g_affine(const Params &P, const Material &mat, float dt, const Mat<D> &F, const Mat<D> &C, float Jp) {
+MPM_HD Mat<D> p2g_affine(const Params &P, const Material &mat, float dt, const Mat<D> &F, const Mat<D> &C, float Jp,
+                         const Mat<D> *rot = nullptr) {
   float e;
   if (mat.kind == KIND_SNOW) e = expf(mat.hardening * (1.0f - Jp));  // :67
   else if (mat.kind == KIND_JELLY) e = mat.hardening;
@@ -484,7 +489,7 @@ MPM_HD Mat<D> p2g_affine(const Params &P, const Material &mat, float dt, const M
   if (mat.kind == KIND_FLUID) {
     PF = mat_diag<D>(lambda * (J - 1) * J);
   } else {
-    Mat<D> r = rotation_of(F);  // :75-76
+    Mat<D> r = rot ? *rot : rotation_of(F);  // :75-76
     PF = mat_add<D>(mat_mul<D>(mat_scale<D>(2 * mu, mat_sub<D>(F, r)), mat_transposed<D>(F)),
                     mat_diag<D>(lambda * (J - 1) * J));  // :81
   }

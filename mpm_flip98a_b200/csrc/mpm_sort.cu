@@ -356,21 +356,29 @@ __global__ void k_flag_chunks(const int *__restrict__ bin_start, int n_bins, int
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b <= n_bins) offs[b] = b < n_bins ? (unsigned)((bin_start[b + 1] - bin_start[b] + cap - 1) / cap) : 0u;
 }
-__global__ void k_fill_chunks(const int *__restrict__ bin_start, int n_bins, int nb_y, int cap,
+__global__ void k_fill_chunks(const int *__restrict__ bin_start, int n_bins, int nb_y, int nb_z, int cap,
                               const unsigned *__restrict__ offs, int4 *__restrict__ chunks) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_bins) return;
   const int s0 = bin_start[b], cnt = bin_start[b + 1] - s0;
-  const int xy = ((b / nb_y) << 16) | (b % nb_y);  // 2D bin coordinates (the only user is the 2D substep kernel)
+  // bin coordinates for the substep kernels: 2D x << 16 | y; 3D x << 20 | y << 10 | z
+  const int xy = nb_z > 0 ? (((b / nb_z) / nb_y) << 20) | (((b / nb_z) % nb_y) << 10) | (b % nb_z)
+                          : ((b / nb_y) << 16) | (b % nb_y);
   unsigned o = offs[b];
-  for (int c0 = 0; c0 < cnt; c0 += cap) chunks[o++] = make_int4(b, s0 + c0, min(cap, cnt - c0), xy);
+  // a bin that needs several chunks is split EVENLY (1024 particles -> 512 + 512, not 768 + 256): the CTAs of the
+  // substep kernel then run for similar times, which is what its static (persistent, strided) work distribution assumes
+  const int parts = (cnt + cap - 1) / cap;  // == what k_flag_chunks reserved
+  for (int j = 0; j < parts; j++) {
+    const int a = (int)((long long)cnt * j / parts), e = (int)((long long)cnt * (j + 1) / parts);
+    chunks[o++] = make_int4(b, s0 + a, e - a, xy);
+  }
 }
 void launch_active_chunks(const int *bin_start, int n_bins, int nb_y, int cap, unsigned *offs, unsigned *scan_tmp,
-                          int4 *chunks, cudaStream_t st) {
+                          int4 *chunks, cudaStream_t st, int nb_z) {
   unsigned blocks = (unsigned)((n_bins + 1 + 255) / 256);
   k_flag_chunks<<<blocks, 256, 0, st>>>(bin_start, n_bins, cap, offs);
   exclusive_scan_u32(offs, (long long)n_bins + 1, scan_tmp, st);  // offs[n_bins] = number of chunks
-  k_fill_chunks<<<blocks, 256, 0, st>>>(bin_start, n_bins, nb_y, cap, offs, chunks);
+  k_fill_chunks<<<blocks, 256, 0, st>>>(bin_start, n_bins, nb_y, nb_z, cap, offs, chunks);
 }
 
 __global__ void k_iota(int *v, long long n) {

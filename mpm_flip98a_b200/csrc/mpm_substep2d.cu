@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
 int substep2d_chunk_capacity() { return CAP; }
 
 #ifndef MPM_SUBSTEP2D_PERSISTENT
-#define MPM_SUBSTEP2D_PERSISTENT 1
+#define MPM_SUBSTEP2D_PERSISTENT 0
 #endif
 void launch_substep2d(const Substep2dArgs &a, bool flip, bool mig, bool resort, cudaStream_t st) {
   if (a.n_chunks <= 0) return;

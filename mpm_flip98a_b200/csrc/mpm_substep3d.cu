@@ -26,12 +26,20 @@ namespace {
 template <bool MIG, bool FLIP, bool RESORT>
 __global__ void __launch_bounds__(128, MPM_G2P3_FAST_MINB) k_g2p3(const __grid_constant__ G2p3Args A) {
   const Params &P = A.P;
-  const long long i = A.first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long n = A.n;
   if (MIG && A.dev_n && n > *A.dev_n) n = *A.dev_n;  // x-slab handles: exact extent on the device
   float vmax = 0.0f;
-  if (i < n) {
-    const float4 xj = A.s.xj[i], vm = A.s.vm[i];
+  // Grid-stride loop with ONE prefetch: the position of a thread's next particle.  A particle's critical chain is two
+  // dependent memory latencies (position -> base cell -> 27 node loads); with the position already in registers only
+  // the node loads remain, and F / v / the next position are in flight beside them.
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = A.first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float4 xj_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (i < n) xj_next = A.s.xj[i];
+  for (; i < n; i += stride) {
+    const float4 xj = xj_next;
+    if (i + stride < n) xj_next = A.s.xj[i + stride];
+    const float4 vm = A.s.vm[i];
     const int mat_id = __float_as_int(vm.w);
     if (!(MIG && mat_id == DEAD)) {  // slot of a particle that emigrated earlier: dropped by the re-sort
       Mat<3> F;
@@ -57,7 +65,7 @@ __global__ void __launch_bounds__(128, MPM_G2P3_FAST_MINB) k_g2p3(const __grid_c
         for (int cc = 0; cc < 3; cc++)
 #pragma unroll
           for (int r = 0; r < 3; r++) C.d[cc][r] = s4 * C.d[cc][r];
-        vmax = fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2])));
+        vmax = fmaxf(vmax, fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2]))));
 #pragma unroll
         for (int k = 0; k < 3; k++) x[k] = x[k] + A.dt * v[k];
         if (FLIP) {
@@ -142,11 +150,340 @@ __global__ void __launch_bounds__(128, MPM_G2P3_FAST_MINB) k_g2p3(const __grid_c
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// The fused 3D substep kernel: G2P of substep n and P2G of substep n+1 in one pass over the particles, one CTA per
+// chunk (<= 512 particles) of a non-empty bin of 4x4x4 cells -- the 3D counterpart of k_substep2d (mpm_substep2d.cu).
+// Reference statements: :134-179 of the current substep, then :53-102 of the next on the state still in registers.
+//   * the G2P half is k_g2p3's body (early stores of C and v, emigrant slot reserved early, on-the-fly re-sort);
+//   * the snow projection hands its rotation factor R to the stress of the next P2G (:75-76) -- F' = R S', so the
+//     2-iteration Newton polar the stand-alone P2G runs on every snow particle is gone (jelly still runs it);
+//   * m C dx waits in the particle's shared-memory record while the projection runs (9 registers less across it);
+//     the stress is added to it afterwards: cs_k = (stress + m C) column k * dx, q = m v - sum_k fx_k cs_k;
+//   * phase 2 = the cell gather of k_p2g_cells<3>: three threads per work item (one stencil row each), 36 register
+//     accumulators, one RED.E.ADD.F32x4 per (item, node); records as four float4 planes.
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef MPM_SUBSTEP3D_MINB
+#define MPM_SUBSTEP3D_MINB 5
+#endif
+constexpr int B3 = 4, NT3 = 128, CAP3 = 512, M3 = 1, L3 = B3 + 2 * M3, NC3 = L3 * L3 * L3;
+constexpr int RM3 = 8, MAXI3 = NC3 + CAP3 / RM3 + 1;
+
+template <bool FLIP, bool MIG, bool RESORT>
+__global__ void __launch_bounds__(NT3, MPM_SUBSTEP3D_MINB) k_substep3d(const __grid_constant__ Substep3dArgs A) {
+  __shared__ float4 recp[4 * CAP3];     // planes: (fx.xyz, q.x) | (q.y, q.z, cs00, cs01) | (cs02, cs10, cs11, cs12) | (cs20, cs21, cs22, -)
+  __shared__ unsigned cr[CAP3];         // (local cell << 16) | rank in cell; 0xffffffff = not binned
+  __shared__ unsigned short sorted[CAP3];
+  __shared__ int cnt[NC3 + 4];          // per-cell count, then record start
+  __shared__ unsigned item[MAXI3];      // cell | first record << 8 | length << 20
+  __shared__ int wtot[4], n_items_sh;
+  const Params &P = A.P;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int4 work = A.chunks[blockIdx.x];
+  const int c0 = work.y, m = work.z;
+  // global cell of local cell 0
+  const int ox = (work.w >> 20) * B3 + P.slab_lo - M3, oy = ((work.w >> 10) & 0x3ff) * B3 - M3, oz = (work.w & 0x3ff) * B3 - M3;
+  const long long n1 = P.n1;
+  const float dxs = P.dx;
+  unsigned n_fallback = 0;
+  float vmax = 0.0f;
+  for (int k = tid; k < NC3; k += NT3) cnt[k] = 0;
+  __syncthreads();
+  // ---------------- phase 1: thread per particle (G2P of this substep, P2G record of the next) ----------------
+  float4 xj_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (tid < m) xj_next = A.s.xj[c0 + tid];
+  for (int i = tid; i < m; i += NT3) {
+    const long long slot_i = (long long)c0 + i;
+    const float4 xj = xj_next;  // issued one iteration ago
+    if (i + NT3 < m) xj_next = A.s.xj[slot_i + NT3];
+    const float4 vm = A.s.vm[slot_i];
+    const int mat_id = __float_as_int(vm.w);
+    if (MIG && mat_id == DEAD) {  // slot of a particle that emigrated earlier; dropped by the re-sort
+      cr[i] = 0xffffffffu;
+      continue;
+    }
+    Mat<3> F;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) F.d[c][r] = A.s.F[c * 3 + r][slot_i];
+    const SoA<3> &out = RESORT ? A.d : A.s;
+    long long dst = slot_i;
+    if (RESORT) dst = (long long)A.new_start[A.key[slot_i]] + A.rank[slot_i];
+    float x[3] = {xj.x, xj.y, xj.z};
+    float Jp = xj.w;
+    const Material &mat = P.mat[material_index(P, mat_id)];
+    float mv[3];
+    int gone_slot = -1;
+    Mat<3> R;
+    bool have_R = false;
+    {
+      // ---- G2P :134-179 ----
+      Stencil<3> st = make_stencil<3>(x, P.inv_dx);
+      clamp_base<3>(P, st.base);  // G2P never flags (P2G did)
+      float v[3], dv[3] = {0.0f, 0.0f, 0.0f};
+      Mat<3> C;
+      gather3_fast(P, st, A.grid_in, A.vold_in, FLIP, v, C, dv);
+      const float s4 = 4 * P.inv_dx;  // the constant of :154, applied once
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) C.d[cc][r] = s4 * C.d[cc][r];
+      vmax = fmaxf(vmax, fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2]))));
+#pragma unroll
+      for (int k = 0; k < 3; k++) x[k] = x[k] + A.dt_g2p * v[k];
+      if (FLIP) {
+        const float a = P.alpha;
+        const float v_in[3] = {vm.x, vm.y, vm.z};
+#pragma unroll
+        for (int k = 0; k < 3; k++) v[k] = (1.0f - a) * v[k] + a * (v_in[k] + dv[k]);
+      }
+      F = mat_mul<3>(mat_add<3>(mat_diag<3>(1.0f), mat_scale<3>(A.dt_g2p, C)), F);
+      // C and v are final: to global memory; m C dx waits in this particle's record for the stress
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) out.C[c * 3 + r][dst] = C.d[c][r];
+      {
+        const float md = P.mass_p * dxs;
+        recp[CAP3 + i] = make_float4(0.0f, 0.0f, md * C.d[0][0], md * C.d[0][1]);
+        recp[2 * CAP3 + i] = make_float4(md * C.d[0][2], md * C.d[1][0], md * C.d[1][1], md * C.d[1][2]);
+        recp[3 * CAP3 + i] = make_float4(md * C.d[2][0], md * C.d[2][1], md * C.d[2][2], 0.0f);
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) mv[k] = P.mass_p * v[k];
+      int side = -1, slot = 0;
+      if (MIG) {
+        const int nbx = max(0, min(base_coord(x[0], P.inv_dx), P.n_grid - 2));
+        if (A.mig.interior) {
+          if ((P.slab_lo > 0 && nbx < P.slab_lo + 2) || (P.slab_hi < P.n_grid && nbx + 4 > P.slab_hi))
+            atomicOr(A.status, STATUS_CFL);
+        } else {
+          side = nbx < P.slab_lo ? 0 : (nbx >= P.slab_hi ? 1 : -1);
+          if (side >= 0) {
+            slot = atomicAdd(&A.mig.count[side], 1);
+            if (slot >= A.mig.cap) {
+              atomicOr(A.status, STATUS_MIGRATION_OVERFLOW);  // stays here (and will be flagged out of slab)
+              side = -1;
+            }
+          }
+        }
+      }
+      out.vm[dst] = make_float4(v[0], v[1], v[2], __int_as_float(side >= 0 ? DEAD : mat_id));
+      if (MIG && side >= 0) gone_slot = slot | (side << 30);
+    }
+    // ---- plasticity (:165-178); snow hands its rotation factor to the next P2G ----
+    if (mat.kind == KIND_SNOW) {
+      const float ratio = plastic_project3(mat.sig_lo, mat.sig_hi, F, &R);  // det(F) / det(F')
+      Jp = clampf(Jp * ratio, P.jp_min, P.jp_max);
+      have_R = true;
+    } else if (mat.kind != KIND_JELLY) {
+      fluid_project(F);
+    }
+    out.xj[dst] = make_float4(x[0], x[1], x[2], Jp);
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) out.F[c * 3 + r][dst] = F.d[c][r];
+    int id = 0;
+    if (RESORT || gone_slot >= 0) id = A.s.id[slot_i];
+    if (RESORT) out.id[dst] = id;
+    if (MIG && gone_slot >= 0) {
+      // the record of an emigrant (layout of emigrate() in mpm_kernels.cu); v and C read back from this thread's stores
+      const int sd = gone_slot >> 30;
+      float *r = (sd == 0 ? A.mig.send_lo : A.mig.send_hi) + (size_t)(gone_slot & 0x3fffffff) * MigRec<3>::WORDS;
+      const float4 vv = out.vm[dst];
+      float rec[MigRec<3>::WORDS];
+      rec[0] = x[0]; rec[1] = x[1]; rec[2] = x[2];
+      rec[3] = vv.x; rec[4] = vv.y; rec[5] = vv.z;
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          rec[6 + c * 3 + k] = F.d[c][k];
+          rec[15 + c * 3 + k] = out.C[c * 3 + k][dst];
+        }
+      rec[24] = Jp;
+      rec[25] = __int_as_float(mat_id);
+      rec[26] = __int_as_float(id);
+      rec[27] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < MigRec<3>::WORDS / 4; k++)
+        reinterpret_cast<float4 *>(r)[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+      cr[i] = 0xffffffffu;  // no P2G here: the receiving handle scatters it when it arrives
+      continue;
+    }
+    {
+      // ---- P2G record of the next substep :53-89 ----
+      Stencil<3> st = make_stencil<3>(x, P.inv_dx);
+      const int bad = clamp_base<3>(P, st.base);
+      if (bad) atomicOr(A.status, bad);
+      const Mat<3> stress = p2g_affine<3>(P, mat, A.dt_p2g, F, mat_zero<3>(), Jp, have_R ? &R : nullptr);  // :67-84 (C = 0)
+      // cs_k = (stress + m C) column k * dx; q = m v - sum_k fx_k cs_k
+      const float4 pb = recp[CAP3 + i], pc = recp[2 * CAP3 + i], pd = recp[3 * CAP3 + i];
+      float cs[3][3] = {{pb.z, pb.w, pc.x}, {pc.y, pc.z, pc.w}, {pd.x, pd.y, pd.z}};
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) cs[k][r] = __fmaf_rn(stress.d[k][r], dxs, cs[k][r]);
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) mv[r] = __fmaf_rn(-st.fx[k], cs[k][r], mv[r]);
+      const int lx = st.base[0] - ox, ly = st.base[1] - oy, lz = st.base[2] - oz;
+      if ((unsigned)lx < (unsigned)L3 && (unsigned)ly < (unsigned)L3 && (unsigned)lz < (unsigned)L3) {
+        const int cell = (lx * L3 + ly) * L3 + lz;
+        const int r = atomicAdd(&cnt[cell], 1);
+        cr[i] = ((unsigned)cell << 16) | (unsigned)r;
+        recp[i] = make_float4(st.fx[0], st.fx[1], st.fx[2], mv[0]);
+        recp[CAP3 + i] = make_float4(mv[1], mv[2], cs[0][0], cs[0][1]);
+        recp[2 * CAP3 + i] = make_float4(cs[0][2], cs[1][0], cs[1][1], cs[1][2]);
+        recp[3 * CAP3 + i] = make_float4(cs[2][0], cs[2][1], cs[2][2], 0.0f);
+      } else {
+        // drifted past the 1-cell bin margin since the last re-sort: per-particle REDs, same separable form
+        cr[i] = 0xffffffffu;
+        n_fallback++;
+        float4 *g0 = A.grid_out + ((long long)(st.base[0] - P.slab_lo) * n1 + st.base[1]) * n1 + st.base[2];
+#pragma unroll 1
+        for (int a = 0; a < 3; a++)
+#pragma unroll 1
+          for (int b = 0; b < 3; b++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+              const float w = st.w[a][0] * st.w[b][1] * st.w[c][2];
+              float val[3];
+#pragma unroll
+              for (int r = 0; r < 3; r++)
+                val[r] = w * __fmaf_rn((float)c, cs[2][r], __fmaf_rn((float)b, cs[1][r], __fmaf_rn((float)a, cs[0][r], mv[r])));
+              atomicAdd(g0 + ((long long)a * n1 + b) * n1 + c, make_float4(val[0], val[1], val[2], w * P.mass_p));
+            }
+      }
+    }
+  }
+  __syncthreads();
+  // ---------------- scans on all four warps (two cells per thread): record starts and work items per cell -----------
+  {
+    const int k0 = 2 * tid, k1 = 2 * tid + 1;
+    const int v0 = k0 < NC3 ? cnt[k0] : 0, v1 = k1 < NC3 ? cnt[k1] : 0;
+    const int parts0 = (v0 + RM3 - 1) / RM3, parts1 = (v1 + RM3 - 1) / RM3;
+    const int p0 = v0 | (parts0 << 16), p1 = v1 | (parts1 << 16);  // both sums stay below 2^16
+    int inc = p0 + p1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) wtot[wid] = inc;
+    __syncthreads();  // also: every count has been read before any is overwritten
+    int pre = 0;
+#pragma unroll
+    for (int w = 0; w < 3; w++)
+      if (w < wid) pre += wtot[w];
+    int ex = pre + inc - (p0 + p1);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int k = h == 0 ? k0 : k1, v = h == 0 ? v0 : v1, parts = h == 0 ? parts0 : parts1;
+      if (k < NC3) {
+        const int start = ex & 0xffff, ifirst = ex >> 16;
+        cnt[k] = start;
+        if (parts > 0) {
+          const int per = parts == 1 ? v : (v + parts - 1) / parts;  // even split
+          for (int sub = 0; sub < parts; sub++) {
+            const int n0 = start + sub * per, len = min(per, v - sub * per);
+            item[ifirst + sub] = (unsigned)k | ((unsigned)n0 << 8) | ((unsigned)len << 20);
+          }
+        }
+      }
+      ex += h == 0 ? p0 : 0;
+    }
+    if (tid == NT3 - 1) n_items_sh = (pre + inc) >> 16;
+  }
+  __syncthreads();
+  const int n_items = n_items_sh;
+  for (int i = tid; i < m; i += NT3) {
+    const unsigned c = cr[i];
+    if (c != 0xffffffffu) sorted[cnt[c >> 16] + (c & 0xffffu)] = (unsigned short)i;
+  }
+  __syncthreads();
+  // ---------------- phase 2: three threads per work item (one stencil row each), 36 register accumulators ----------
+  for (int t3 = tid; t3 < n_items * 3; t3 += NT3) {
+    const int it = t3 / 3, a = t3 - it * 3;  // the three rows of an item sit in adjacent lanes: their record reads broadcast
+    const unsigned ds = item[it];
+    const int cell = ds & 0xff, n0 = (ds >> 8) & 0xfff, len = ds >> 20;
+    f2 acc_xy[3][3], acc_zm[3][3];
+#pragma unroll
+    for (int b = 0; b < 3; b++)
+#pragma unroll
+      for (int c = 0; c < 3; c++) acc_xy[b][c] = acc_zm[b][c] = sp2(0.0f);
+    for (int jj = n0; jj < n0 + len; jj++) {
+      const int i = sorted[jj];
+      const float4 ra = recp[i], rb = recp[CAP3 + i], rc = recp[2 * CAP3 + i], rd = recp[3 * CAP3 + i];
+      const float fx[3] = {ra.x, ra.y, ra.z};
+      float w[3][3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {  // the three expressions of :61-63
+        w[0][k] = 0.5f * ((1.5f - fx[k]) * (1.5f - fx[k]));
+        w[1][k] = 0.75f - ((fx[k] - 1.0f) * (fx[k] - 1.0f));
+        w[2][k] = 0.5f * ((fx[k] - 0.5f) * (fx[k] - 0.5f));
+      }
+      // node value = w_abc * (Q + a CS_0 + b CS_1 + c CS_2) with Q = (q, mass_p), CS_k = (cs_k, 0): two FFMA2 per step
+      const f2 cs_xy[3] = {mk2(rb.z, rb.w), mk2(rc.y, rc.z), mk2(rd.x, rd.y)};
+      const f2 cs_zm[3] = {mk2(rc.x, 0.0f), mk2(rc.w, 0.0f), mk2(rd.z, 0.0f)};
+      const f2 q_xy = mk2(ra.w, rb.x), q_zm = mk2(rb.y, P.mass_p);
+      const float wa = a == 0 ? w[0][0] : (a == 1 ? w[1][0] : w[2][0]);
+      const f2 xa_xy = fma2(sp2((float)a), cs_xy[0], q_xy), xa_zm = fma2(sp2((float)a), cs_zm[0], q_zm);
+#pragma unroll
+      for (int b = 0; b < 3; b++) {
+        const float wab = wa * w[b][1];
+        const f2 yb_xy = b == 0 ? xa_xy : (b == 1 ? add2(xa_xy, cs_xy[1]) : fma2(sp2(2.0f), cs_xy[1], xa_xy));
+        const f2 yb_zm = b == 0 ? xa_zm : (b == 1 ? add2(xa_zm, cs_zm[1]) : fma2(sp2(2.0f), cs_zm[1], xa_zm));
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float wabc = wab * w[c][2];
+          const f2 z_xy = c == 0 ? yb_xy : (c == 1 ? add2(yb_xy, cs_xy[2]) : fma2(sp2(2.0f), cs_xy[2], yb_xy));
+          const f2 z_zm = c == 0 ? yb_zm : (c == 1 ? add2(yb_zm, cs_zm[2]) : fma2(sp2(2.0f), cs_zm[2], yb_zm));
+          acc_xy[b][c] = fma2(sp2(wabc), z_xy, acc_xy[b][c]);
+          acc_zm[b][c] = fma2(sp2(wabc), z_zm, acc_zm[b][c]);
+        }
+      }
+    }
+    const int lx = cell / (L3 * L3), ly = (cell / L3) % L3, lz = cell % L3;
+    float4 *gp = A.grid_out + ((long long)(ox + lx + a - P.slab_lo) * n1 + (oy + ly)) * n1 + (oz + lz);
+#pragma unroll
+    for (int b = 0; b < 3; b++)
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+        atomicAdd(gp + b * n1 + c, make_float4(acc_xy[b][c].x, acc_xy[b][c].y, acc_zm[b][c].x, acc_zm[b][c].y));  // RED.E.ADD.F32x4
+  }
+  if (A.stats) {
+    if (n_fallback) {
+      atomicAdd(&A.stats[0], (unsigned long long)n_fallback);
+      atomicAdd(&A.stats[1], (unsigned long long)n_fallback);
+    }
+    const unsigned bits = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax * A.dt_g2p * P.inv_dx));
+    unsigned *slot = reinterpret_cast<unsigned *>(&A.stats[2]);
+    if (lane == 0 && bits > *reinterpret_cast<volatile unsigned *>(slot)) atomicMax(slot, bits);
+  }
+}
+
 }  // namespace
 
+#ifndef MPM_G2P3_WAVES
+#define MPM_G2P3_WAVES 4  // CTAs per resident slot: a few waves keep the tail short, the rest is the grid-stride loop
+#endif
 void launch_g2p3(const G2p3Args &a, bool flip, bool mig, bool resort, cudaStream_t st) {
   if (a.n - a.first <= 0) return;
-  const unsigned blocks = (unsigned)((a.n - a.first + 127) / 128);
+  unsigned blocks = (unsigned)((a.n - a.first + 127) / 128);
+  if (MPM_G2P3_WAVES > 0) {
+    static int sms[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64) {
+      if (!sms[dev]) cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev);
+      const unsigned cap = (unsigned)(sms[dev] > 0 ? sms[dev] : 148) * MPM_G2P3_FAST_MINB * MPM_G2P3_WAVES;
+      if (blocks > cap) blocks = cap;
+    }
+  }
 #define MPM_G3(F_, M_, R_) k_g2p3<F_, M_, R_><<<blocks, 128, 0, st>>>(a)
   // template order: MIG, FLIP, RESORT
   if (mig) {
@@ -159,4 +496,21 @@ void launch_g2p3(const G2p3Args &a, bool flip, bool mig, bool resort, cudaStream
 #undef MPM_G3
 }
 
+}  // namespace mpm
+
+namespace mpm {
+int substep3d_chunk_capacity() { return 512; }
+void launch_substep3d(const Substep3dArgs &a, bool flip, bool mig, bool resort, cudaStream_t st) {
+  const int grid = a.n_chunks;
+  if (grid <= 0) return;
+#define MPM_S3D(F_, M_, R_) k_substep3d<F_, M_, R_><<<grid, 128, 0, st>>>(a)
+  if (flip) {
+    if (mig) { if (resort) MPM_S3D(true, true, true); else MPM_S3D(true, true, false); }
+    else     { if (resort) MPM_S3D(true, false, true); else MPM_S3D(true, false, false); }
+  } else {
+    if (mig) { if (resort) MPM_S3D(false, true, true); else MPM_S3D(false, true, false); }
+    else     { if (resort) MPM_S3D(false, false, true); else MPM_S3D(false, false, false); }
+  }
+#undef MPM_S3D
+}
 }  // namespace mpm
