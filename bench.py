@@ -239,6 +239,7 @@ def main():
     ap.add_argument("--e2e-calls", type=int, default=2)
     ap.add_argument("--naive", action="store_true", help="one-thread-per-particle kernels (MPM_FLAG_NAIVE)")
     ap.add_argument("--no-fuse", action="store_true", help="separate P2G and G2P kernels (MPM_FLAG_NO_FUSE)")
+    ap.add_argument("--fuse-3d", action="store_true", help="3D: the fused G2P->P2G kernel (MPM_FLAG_FUSE_3D, opt-in)")
     ap.add_argument("--no-overlap", action="store_true",
                     help="N > 1: plain slab schedule (default: interior bins on a side stream while the slab boundary "
                          "is exchanged, MPM_FLAG_OVERLAP)")
@@ -283,7 +284,7 @@ def main():
     host_out = torch.empty_like(host, pin_memory=True)
 
     stream = torch.cuda.Stream()
-    flags = FLAG_NAIVE if args.naive else (16 if args.no_fuse else 0)
+    flags = FLAG_NAIVE if args.naive else ((16 if args.no_fuse else 0) | (128 if args.fuse_3d else 0))
     with torch.cuda.stream(stream):
         eng = mpm.Engine(dim=dim, n_grid=n_grid, capacity=n, dt=dt, vol_p=vol, alpha=alpha, device=local,
                          flags=flags, stream=stream.cuda_stream, rebin_every=args.rebin_every)
@@ -559,7 +560,8 @@ def run_slabs(args, rank, world, local):
     # with the overlapped schedule the engine's interior launch runs on a lowest-priority side stream; the main stream
     # (boundary bins, exchange helpers) and NCCL's own stream (TORCH_NCCL_HIGH_PRIORITY, set in __main__) outrank it
     stream = torch.cuda.Stream(priority=-1) if overlap else torch.cuda.Stream()
-    flags = FLAG_NAIVE if args.naive else ((FLAG_OVERLAP if overlap else 0) | (16 if args.no_fuse else 0))
+    flags = FLAG_NAIVE if args.naive else ((FLAG_OVERLAP if overlap else 0) | (16 if args.no_fuse else 0) |
+                                           (128 if args.fuse_3d else 0))
     PH = ("clear", "p2g", "grid", "g2p", "bin", "halo", "migrate")
 
     def setup(slabs):

@@ -56,7 +56,8 @@ enum {
                                          (measured no faster than the read-only-path gather: off by default) */
   MPM_FLAG_NO_FUSE = 1 << 4,          /* keep P2G and G2P as separate kernels (2D default, single GPU and
                                          x-slabs alike: G2P of a substep and P2G of the next run as ONE
-                                         kernel, one particle read + one write per substep; 3D is unfused) */
+                                         kernel, one particle read + one write per substep; 3D runs two kernels
+                                         unless MPM_FLAG_FUSE_3D) */
   MPM_FLAG_OVERLAP = 1 << 5,          /* x-slab handles on the fused schedule: bins >= 2 bin columns away from the
                                          slab cuts run on a side stream while the boundary bins finish first, so
                                          the caller's migration / halo exchange overlaps the interior compute */
@@ -67,6 +68,10 @@ enum {
                                          the grid after P2G (total mass included) is BITWISE the CPU oracle's on the
                                          same particle order.  Exact association throughout; whole-domain handles
                                          only; a validation mode, ~10x slower. */
+  MPM_FLAG_FUSE_3D = 1 << 7,          /* 3D: G2P of a substep and P2G of the next as ONE kernel (k_substep3d: the snow
+                                         projection hands its rotation factor to the stress).  Correct and tested, but
+                                         measured no faster on B200 than the two 3D kernels (3.34 vs 3.23 ms on the 256^3
+                                         scene: 96 registers leave 5 CTAs per SM): opt-in */
   MPM_FLAG_STRICT = 1 << 2            /* binned path: P2G node contributions (:92-100) and the G2P gather
                                          (:153-154) keep the reference's exact association instead of the
                                          separable / hoisted FMA forms (algebraically identical, ~1e-7

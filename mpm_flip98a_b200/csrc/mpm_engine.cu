@@ -228,7 +228,7 @@ struct mpm_handle {
   bool fast3d() const {
     return binned && D == 3 && !fused && !(cfg.flags & (MPM_FLAG_STRICT | MPM_FLAG_G2P_TILE));
   }
-  // 3D default: G2P and the next P2G in ONE kernel (k_substep3d); MPM_FLAG_NO_FUSE keeps the two kernels above
+  // MPM_FLAG_FUSE_3D: G2P and the next P2G in ONE kernel (k_substep3d)
   bool fast3f() const { return fused && D == 3; }
   bool resorts_on_the_fly() const { return fast2d() || fast3d() || fast3f(); }
   int chunk_capacity() const { return D == 2 ? substep2d_chunk_capacity() : substep3d_chunk_capacity(); }
@@ -424,9 +424,10 @@ int mpm_handle::init() {
       return rc;
   }
   // 2D only: in 3D the Jacobi-SVD-heavy kernels are compute-bound and fusing them costs occupancy (measured slower)
-  // fused G2P->P2G: 2D k_substep2d (MPM_FLAG_STRICT: the generic k_p2g_cells<FUSED>), 3D k_substep3d (3D + STRICT stays
-  // unfused: the exact-association generic kernel spills when fused)
-  fused = binned && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE)) && (D == 2 || !(cfg.flags & MPM_FLAG_STRICT));
+  // fused G2P->P2G: 2D k_substep2d (MPM_FLAG_STRICT: the generic k_p2g_cells<FUSED>); 3D only on request
+  // (MPM_FLAG_FUSE_3D: k_substep3d, measured no faster than the two 3D kernels; 3D + STRICT always stays unfused)
+  fused = binned && !(cfg.flags & (MPM_FLAG_NO_FUSE | MPM_FLAG_G2P_TILE)) &&
+          (D == 2 || ((cfg.flags & MPM_FLAG_FUSE_3D) && !(cfg.flags & MPM_FLAG_STRICT)));
   pipelined = fused || multi;
   if (pipelined)
     if ((rc = dalloc(&grid_next, (size_t)nodes))) return rc;

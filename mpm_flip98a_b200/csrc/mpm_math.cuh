@@ -292,7 +292,8 @@ MPM_HD Mat<3> rotation_of_svd(const Mat<3> &F) {
 
 // Device: reciprocal square root / division by the special-function unit (<= 2 ulp) in the 3D decompositions: the Jacobi rotations of
 // plastic_project3 (a rotation angle that is off by an ulp leaves an off-diagonal of ~1e-7 |apq| behind, far below
-// what the next sweep tests for) and the 0.5 / det of the Newton polar iteration (self-correcting).  Host (tests/host_check.cpp): the oracle's exact statements.
+// what the next sweep tests for).  The Newton polar iteration stays exact: it feeds P2G, which the deterministic mode
+// promises bitwise.  Host (tests/host_check.cpp): the oracle's exact statements.
 #if defined(__CUDA_ARCH__)
 #define MPM_RSQRT(x) rsqrtf(x)
 #define MPM_FDIV(a, b) __fdividef((a), (b))
@@ -327,7 +328,7 @@ MPM_HD bool polar_newton3(const Mat<3> &F, Mat<3> &X) {
     K.d[2][0] = cof(a[1], b[2], a[2], b[1]); K.d[2][1] = cof(a[2], b[0], a[0], b[2]); K.d[2][2] = cof(a[0], b[1], a[1], b[0]);
     const float det = fmaf(a[2], K.d[0][2], fmaf(a[1], K.d[0][1], a[0] * K.d[0][0]));
     if (!(det > 1e-6f * scale * scale * scale)) return false;
-    const float h = MPM_FDIV(0.5f, det);
+    const float h = 0.5f / det;  // exact: MPM_FLAG_DETERMINISTIC promises a P2G grid bitwise the oracle's
     float delta = 0.0f;
 #pragma unroll
     for (int cc = 0; cc < 3; cc++)

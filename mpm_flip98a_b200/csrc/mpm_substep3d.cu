@@ -344,9 +344,9 @@ __global__ void __launch_bounds__(NT3, MPM_SUBSTEP3D_MINB) k_substep3d(const __g
         cr[i] = 0xffffffffu;
         n_fallback++;
         float4 *g0 = A.grid_out + ((long long)(st.base[0] - P.slab_lo) * n1 + st.base[1]) * n1 + st.base[2];
-#pragma unroll 1
+#pragma unroll  // (fully unrolled: a run-time index into st.w would move the stencil to local memory for EVERY particle)
         for (int a = 0; a < 3; a++)
-#pragma unroll 1
+#pragma unroll
           for (int b = 0; b < 3; b++)
 #pragma unroll
             for (int c = 0; c < 3; c++) {
@@ -469,7 +469,8 @@ __global__ void __launch_bounds__(NT3, MPM_SUBSTEP3D_MINB) k_substep3d(const __g
 }  // namespace
 
 #ifndef MPM_G2P3_WAVES
-#define MPM_G2P3_WAVES 4  // CTAs per resident slot: a few waves keep the tail short, the rest is the grid-stride loop
+#define MPM_G2P3_WAVES 0  // > 0: cap the grid at this many CTAs per resident slot, the rest is the grid-stride loop with the
+                          // position prefetch.  Measured on c5: 4 waves 1.60 ms, uncapped (one particle per thread) 1.52 ms
 #endif
 void launch_g2p3(const G2p3Args &a, bool flip, bool mig, bool resort, cudaStream_t st) {
   if (a.n - a.first <= 0) return;

@@ -21,6 +21,7 @@ FLAG_G2P_TILE = 8
 FLAG_NO_FUSE = 16
 FLAG_OVERLAP = 32
 FLAG_DETERMINISTIC = 64
+FLAG_FUSE_3D = 128
 
 _ERRORS = {-1: "MPM_E_INVALID", -2: "MPM_E_CUDA", -3: "MPM_E_CAPACITY", -4: "MPM_E_DOMAIN", -5: "MPM_E_CFL",
            -6: "MPM_E_STATE"}

@@ -12,7 +12,8 @@ import pytest
 
 import mpm_flip98a_b200 as mpm
 from mpm_flip98a_b200 import scenes
-from mpm_flip98a_b200.engine import FLAG_CAPTURE_POST_P2G, FLAG_G2P_TILE, FLAG_NAIVE, FLAG_NO_FUSE, FLAG_STRICT
+from mpm_flip98a_b200.engine import (FLAG_CAPTURE_POST_P2G, FLAG_FUSE_3D, FLAG_G2P_TILE, FLAG_NAIVE, FLAG_NO_FUSE,
+                                     FLAG_STRICT)
 from oracle.cpu import make_params
 from tests.util import bits, fields, rel_l2
 
@@ -92,7 +93,7 @@ def test_three_materials_one_warm_substep(oracle, alpha, flags):
     check_one_step(oracle, p, 2, 80, 1e-4, 1.0, alpha, flags)
 
 
-@pytest.mark.parametrize("flags", MODES)
+@pytest.mark.parametrize("flags", MODES + [FLAG_FUSE_3D])
 @pytest.mark.parametrize("alpha", [0.0, 0.95])
 def test_3d_one_warm_substep(oracle, alpha, flags):
     n = 32
@@ -273,7 +274,7 @@ def test_changing_dt_between_calls(oracle, flags):
         assert rel_l2(fg[k], fw[k]) <= 2e-5, (k, rel_l2(fg[k], fw[k]))  # 10 substeps of <= 1e-5 noise each, not additive
 
 
-@pytest.mark.parametrize("flags", [FLAG_NAIVE, 0])
+@pytest.mark.parametrize("flags", [FLAG_NAIVE, 0, FLAG_FUSE_3D])
 def test_3d_many_substeps_bulk(oracle, flags):
     # 3D lift over 300 substeps on a well-conditioned scene (elastic slab settling): bulk diagnostics vs the oracle
     n = 32

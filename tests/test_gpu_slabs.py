@@ -7,7 +7,7 @@ import pytest
 
 import mpm_flip98a_b200 as mpm
 from mpm_flip98a_b200 import parallel, scenes
-from mpm_flip98a_b200.engine import FLAG_NAIVE, FLAG_NO_FUSE
+from mpm_flip98a_b200.engine import FLAG_FUSE_3D, FLAG_NAIVE, FLAG_NO_FUSE
 from oracle.cpu import make_params
 from tests.util import bits, fields, rel_l2
 
@@ -41,7 +41,7 @@ def test_one_warm_substep_matches_oracle(oracle, shipped, world, flags):
     assert np.array_equal(bits(got[:, -1]), bits(p[:, -1]))
 
 
-@pytest.mark.parametrize("flags", [FLAG_NAIVE, 0, FLAG_NO_FUSE])
+@pytest.mark.parametrize("flags", [FLAG_NAIVE, 0, FLAG_NO_FUSE, FLAG_FUSE_3D])
 def test_3d_slabs_one_warm_substep(oracle, flags):
     n = 32
     dt, vol = scenes.scaled_constants(n)
@@ -176,3 +176,31 @@ def test_run_continues_unsettled_and_changes_dt(oracle, flags):
     assert rel_l2(got[:, 0:2], single[:, 0:2]) <= 1e-4 and rel_l2(got[:, 2:4], single[:, 2:4]) <= 1e-3
     b0, b1 = scenes.bulk(single, 2), scenes.bulk(got, 2)
     assert abs(b0["ke"] - b1["ke"]) <= 1e-3 * b0["ke"]
+
+
+def test_overlapped_schedule_3d(oracle):
+    """MPM_FLAG_OVERLAP with the fused 3D substep kernel: two slabs of 8 bin columns each (64^3 grid), interior chunks
+    on the side stream; one warm substep against the oracle, then 40 substeps with re-sorts against the plain schedule."""
+    from mpm_flip98a_b200.engine import FLAG_OVERLAP
+    FLAG_OVERLAP |= FLAG_FUSE_3D  # the overlapped schedule splits the fused kernel's work list
+    n = 64
+    dt, vol = scenes.scaled_constants(n, 3)
+    p = scenes.collapse_3d(n, per_side=2, y_top=0.4, xz=(0.1, 0.9))
+    p[:, 3] = np.where(p[:, 1] > 0.2, 2.0, -2.0).astype(np.float32)  # shear along x: particles cross the cut both ways
+    with mpm.Engine(dim=3, n_grid=n, capacity=len(p), dt=dt, vol_p=vol) as e:
+        e.upload(p)
+        e.substep(60)
+        warm = e.read()
+    P = make_params(dim=3, n_grid=n, vol_p=vol)
+    want = warm.copy()
+    oracle.advance(P, dt, want, 1)
+    got, status, counts, slabs = run_slabs(warm, 3, n, 2, 1, dt, vol, flags=FLAG_OVERLAP, shared_stream=True)
+    assert status == [0, 0] and sum(counts) == len(p)
+    fw, fg = fields(want, 3), fields(got, 3)
+    for k in fw:
+        assert rel_l2(fg[k], fw[k]) <= 1e-5, (k, rel_l2(fg[k], fw[k]))
+    a, sa, ca, _ = run_slabs(warm, 3, n, 2, 40, dt, vol, flags=FLAG_OVERLAP, rebin_every=8, shared_stream=True)
+    b, sb_, cb, _ = run_slabs(warm, 3, n, 2, 40, dt, vol, flags=0, rebin_every=8)  # the default two-kernel 3D path
+    assert sa == [0, 0] and sb_ == [0, 0] and sum(ca) == len(p) and sum(cb) == len(p)
+    assert (parallel.owner_of(warm[:, 0], n, slabs) != parallel.owner_of(a[:, 0], n, slabs)).sum() > 100
+    assert rel_l2(a[:, 0:3], b[:, 0:3]) <= 1e-5 and rel_l2(a[:, 3:6], b[:, 3:6]) <= 1e-3
