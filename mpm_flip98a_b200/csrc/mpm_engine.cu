@@ -431,7 +431,7 @@ int mpm_handle::init() {
   pipelined = fused || multi;
   if (pipelined)
     if ((rc = dalloc(&grid_next, (size_t)nodes))) return rc;
-  if (fast3f()) {  // work list of the fused 3D kernel
+  if (D == 3 && binned) {  // work list of the 3D chunk kernels (k_g2p3_tile, k_substep3d)
     chunks_cap = (long long)G.n_bins + cap / chunk_capacity() + 2;
     for (int b = 0; b < 2; b++)
       if ((rc = dalloc(&chunks_buf[b], (size_t)chunks_cap))) return rc;
@@ -978,6 +978,16 @@ int mpm_handle::step_grid_g2p(float dt) {
       ga.status = status_dev;
       ga.stats = stats_dev;
       ga.dev_n = dev_ext;
+      ga.chunks = chunks_buf[bs];
+      ga.n_chunks = n_chunks;
+#ifndef MPM_G2P3_TILE
+#define MPM_G2P3_TILE 1
+#endif
+      if (MPM_G2P3_TILE && chunk_offs) {
+        // binned range: CTA per chunk with the node tile in shared memory; immigrant tail: thread per particle
+        launch_g2p3_tile(ga, P.alpha != 0.0f, mig.enabled != 0, resort3, stream);
+        ga.first = n_binned;
+      }
       launch_g2p3(ga, P.alpha != 0.0f, mig.enabled != 0, resort3, stream);
       if (resort3) {
         if (multi)  // the new extent (dead slots dropped) = first slot of the "dead" bin of the new order

@@ -11,8 +11,13 @@ namespace mpm {
 // ~190 instructions instead of ~680 for the node-by-node form; fused multiply-adds, algebraically identical
 // (~1e-7 relative from the reference association; MPM_FLAG_STRICT / MPM_FLAG_NAIVE keep g2p_accumulate).
 // C comes back without the constant 4*inv_dx; with FLIP, dv = v - sum w vold.
-__device__ __forceinline__ void gather3_fast(const Params &P, const Stencil<3> &st, const float4 *__restrict__ grid,
-                                             const float4 *__restrict__ vold, bool flip, float *v, Mat<3> &C, float *dv) {
+// `gbase` / `obase` point at node (base, base, base) of the particle; stride_a / stride_b = distance (in nodes) between
+// x-planes and y-rows: (n1*n1, n1) for the global grid, the padded tile strides for a shared-memory tile
+// (LDG = false: plain loads, the tile is not read-only data).
+template <bool LDG>
+__device__ __forceinline__ void gather3_rows(const Stencil<3> &st, const float4 *__restrict__ gbase, const float4 *__restrict__ obase,
+                                             long long stride_a, long long stride_b, bool flip, float *v, Mat<3> &C,
+                                             float *dv) {
   float wd[3][3];  // w * (k - fx) per axis
 #pragma unroll
   for (int k = 0; k < 3; k++)
@@ -20,16 +25,14 @@ __device__ __forceinline__ void gather3_fast(const Params &P, const Stencil<3> &
     for (int ax = 0; ax < 3; ax++) wd[k][ax] = st.w[k][ax] * ((float)k - st.fx[ax]);
   f2 vxy = sp2(0.0f), c0xy = sp2(0.0f), c1xy = sp2(0.0f), c2xy = sp2(0.0f), oxy = sp2(0.0f);
   float vz = 0.0f, c0z = 0.0f, c1z = 0.0f, c2z = 0.0f, oz = 0.0f;
-  const long long n1 = P.n1;
-  const long long node0 = ((long long)(st.base[0] - P.slab_lo) * n1 + st.base[1]) * n1 + st.base[2];
 #pragma unroll
   for (int a = 0; a < 3; a++) {
     f2 Txy = sp2(0.0f), Uyxy = sp2(0.0f), Uzxy = sp2(0.0f), Oxy = sp2(0.0f);
     float Tz = 0.0f, Uyz = 0.0f, Uzz = 0.0f, Oz = 0.0f;
 #pragma unroll
     for (int b = 0; b < 3; b++) {
-      const float4 *row = grid + node0 + (a * n1 + b) * n1;
-      const float4 g0 = __ldg(row), g1 = __ldg(row + 1), g2 = __ldg(row + 2);
+      const float4 *row = gbase + a * stride_a + b * stride_b;
+      const float4 g0 = LDG ? __ldg(row) : row[0], g1 = LDG ? __ldg(row + 1) : row[1], g2 = LDG ? __ldg(row + 2) : row[2];
       f2 txy = mul2(sp2(st.w[0][2]), mk2(g0.x, g0.y));
       txy = fma2(sp2(st.w[1][2]), mk2(g1.x, g1.y), txy);
       txy = fma2(sp2(st.w[2][2]), mk2(g2.x, g2.y), txy);
@@ -45,8 +48,8 @@ __device__ __forceinline__ void gather3_fast(const Params &P, const Stencil<3> &
       Uzxy = fma2(sp2(st.w[b][1]), uxy, Uzxy);
       Uzz = fmaf(st.w[b][1], uz, Uzz);
       if (flip) {
-        const float4 *ro = vold + node0 + (a * n1 + b) * n1;
-        const float4 o0 = __ldg(ro), o1 = __ldg(ro + 1), o2 = __ldg(ro + 2);
+        const float4 *ro = obase + a * stride_a + b * stride_b;
+        const float4 o0 = LDG ? __ldg(ro) : ro[0], o1 = LDG ? __ldg(ro + 1) : ro[1], o2 = LDG ? __ldg(ro + 2) : ro[2];
         f2 pxy = mul2(sp2(st.w[0][2]), mk2(o0.x, o0.y));
         pxy = fma2(sp2(st.w[1][2]), mk2(o1.x, o1.y), pxy);
         pxy = fma2(sp2(st.w[2][2]), mk2(o2.x, o2.y), pxy);
@@ -75,6 +78,14 @@ __device__ __forceinline__ void gather3_fast(const Params &P, const Stencil<3> &
   if (flip) {
     dv[0] = vxy.x - oxy.x; dv[1] = vxy.y - oxy.y; dv[2] = vz - oz;
   }
+}
+
+// the global-grid form (read-only path)
+__device__ __forceinline__ void gather3_fast(const Params &P, const Stencil<3> &st, const float4 *__restrict__ grid,
+                                             const float4 *__restrict__ vold, bool flip, float *v, Mat<3> &C, float *dv) {
+  const long long n1 = P.n1;
+  const long long node0 = ((long long)(st.base[0] - P.slab_lo) * n1 + st.base[1]) * n1 + st.base[2];
+  gather3_rows<true>(st, grid + node0, flip ? vold + node0 : nullptr, n1 * n1, n1, flip, v, C, dv);
 }
 
 }  // namespace mpm

@@ -355,6 +355,9 @@ __device__ __forceinline__ void red_node(const Params &P, float4 *grid, int i, i
 #ifndef MPM_P2G_MINB3
 #define MPM_P2G_MINB3 6
 #endif
+#ifndef MPM_P2G3_PREFETCH
+#define MPM_P2G3_PREFETCH 0
+#endif
 #ifndef MPM_FUSED_MINB
 #define MPM_FUSED_MINB 7
 #endif
@@ -405,6 +408,11 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
     // current one (measured on c4: 8.65 -> 7.73 ms; memory latency was the top stall reason)
     PState<D> nxt;
     if (FUSED && tid < m) load_g2p(s, (long long)c0 + tid, nxt, P.alpha != 0.0f);
+    // 3D stand-alone P2G: the same software pipeline -- position, velocity / material and F of the thread's next
+    // particle are in flight while the current one runs its Newton polar; C is only needed at the very end of the
+    // record (:89) and is loaded per particle without anyone waiting for it
+    constexpr bool PF3 = MPM_P2G3_PREFETCH && !FUSED && D == 3;
+    if (PF3 && tid < m) load_g2p(s, (long long)c0 + tid, nxt, true);
     for (int i = tid; i < m; i += NT) {
       PState<D> p;
       if (FUSED) {
@@ -431,6 +439,13 @@ __global__ void __launch_bounds__(NT, FUSED ? MPM_FUSED_MINB : (D == 3 ? MPM_P2G
         } else {
           store_state(s, (long long)c0 + i, p);
         }
+      } else if constexpr (PF3) {
+        p = nxt;
+        if (i + NT < m) load_g2p(s, (long long)c0 + i + NT, nxt, true);
+#pragma unroll
+        for (int c = 0; c < D; c++)
+#pragma unroll
+          for (int r = 0; r < D; r++) p.C.d[c][r] = s.C[c * D + r][(long long)c0 + i];
       } else {
         load_full(s, (long long)c0 + i, p);
       }

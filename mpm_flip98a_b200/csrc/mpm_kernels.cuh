@@ -102,8 +102,11 @@ struct G2p3Args {
   int *status;
   unsigned long long *stats;
   const int *dev_n;           // x-slab handles: exact storage extent on the device
+  const int4 *chunks;         // launch_g2p3_tile: work list (bin, first slot, particles, bin x << 20 | y << 10 | z)
+  int n_chunks;
 };
-void launch_g2p3(const G2p3Args &a, bool flip, bool mig, bool resort, cudaStream_t st);
+void launch_g2p3(const G2p3Args &a, bool flip, bool mig, bool resort, cudaStream_t st);       // thread per particle
+void launch_g2p3_tile(const G2p3Args &a, bool flip, bool mig, bool resort, cudaStream_t st);  // CTA per chunk, smem tile
 
 // ---- the fused 3D substep kernel (mpm_substep3d.cu): G2P -> P2G in one pass, optional on-the-fly re-sort ----
 struct Substep3dArgs {

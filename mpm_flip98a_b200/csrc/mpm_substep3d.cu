@@ -23,15 +23,137 @@ namespace {
 #define MPM_G2P3_FAST_MINB 7
 #endif
 
+// tile of node velocities a CTA of k_g2p3_tile stages in shared memory: the bin's 4^3 base cells + 1-cell drift margin
+// + stencil reach = 8 nodes per axis; z rows padded to 9 float4 (144 B) so that neighbouring y rows do not share banks
+constexpr int TN = 8, TZ = 9, TILE_NODES = TN * TN * TZ;
+
+// One particle of the 3D G2P (:134-179).  TILE: gather from the shared-memory tile whose node (0,0,0) is the global
+// node (tox, toy, toz) when the stencil lies inside it, else (drifted past the margin: rare) from global memory.
+template <bool MIG, bool FLIP, bool RESORT, bool TILE>
+__device__ __forceinline__ void g2p3_particle(const G2p3Args &A, long long i, float4 xj, float4 vm, Mat<3> F,
+                                              const float4 *tile, const float4 *tile_o, int tox, int toy, int toz,
+                                              float &vmax) {
+  const Params &P = A.P;
+  const int mat_id = __float_as_int(vm.w);
+  const SoA<3> &out = RESORT ? A.d : A.s;
+  long long dst = i;
+  if (RESORT) dst = (long long)A.new_start[A.key[i]] + A.rank[i];
+  float x[3] = {xj.x, xj.y, xj.z};
+  float Jp = xj.w;
+  const Material &mat = P.mat[material_index(P, mat_id)];
+  // ---- gather (:136-156), advect (:159), F update (:162) ----
+  Stencil<3> st = make_stencil<3>(x, P.inv_dx);
+  clamp_base<3>(P, st.base);  // G2P never flags (P2G did)
+  float v[3], dv[3] = {0.0f, 0.0f, 0.0f};
+  Mat<3> C;
+  bool from_tile = false;
+  if (TILE) {
+    const int l0 = st.base[0] - tox, l1 = st.base[1] - toy, l2 = st.base[2] - toz;
+    from_tile = (unsigned)l0 <= (unsigned)(TN - 3) && (unsigned)l1 <= (unsigned)(TN - 3) && (unsigned)l2 <= (unsigned)(TN - 3);
+    if (from_tile) {
+      const int at = (l0 * TN + l1) * TZ + l2;
+      gather3_rows<false>(st, tile + at, tile_o + at, TN * TZ, TZ, FLIP, v, C, dv);
+    }
+  }
+  if (!from_tile) gather3_fast(P, st, A.grid, A.vold, FLIP, v, C, dv);
+  const float s4 = 4 * P.inv_dx;  // the constant of :154, applied once
+#pragma unroll
+  for (int cc = 0; cc < 3; cc++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) C.d[cc][r] = s4 * C.d[cc][r];
+  vmax = fmaxf(vmax, fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2]))));
+#pragma unroll
+  for (int k = 0; k < 3; k++) x[k] = x[k] + A.dt * v[k];
+  if (FLIP) {
+    const float a = P.alpha;
+    const float v_in[3] = {vm.x, vm.y, vm.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) v[k] = (1.0f - a) * v[k] + a * (v_in[k] + dv[k]);
+  }
+  F = mat_mul<3>(mat_add<3>(mat_diag<3>(1.0f), mat_scale<3>(A.dt, C)), F);
+  // ---- C and v are final: out they go ----
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) out.C[c * 3 + r][dst] = C.d[c][r];
+  // x-slab runs: a particle whose NEW base column left the slab reserves its slot in that side's message
+  int side = -1, slot = 0;
+  if (MIG) {
+    const int nbx = max(0, min(base_coord(x[0], P.inv_dx), P.n_grid - 2));
+    if (A.mig.interior) {
+      if ((P.slab_lo > 0 && nbx < P.slab_lo + 2) || (P.slab_hi < P.n_grid && nbx + 4 > P.slab_hi))
+        atomicOr(A.status, STATUS_CFL);
+    } else {
+      side = nbx < P.slab_lo ? 0 : (nbx >= P.slab_hi ? 1 : -1);
+      if (side >= 0) {
+        slot = atomicAdd(&A.mig.count[side], 1);
+        if (slot >= A.mig.cap) {
+          atomicOr(A.status, STATUS_MIGRATION_OVERFLOW);  // stays here (and will be flagged out of slab)
+          side = -1;
+        }
+      }
+    }
+  }
+  out.vm[dst] = make_float4(v[0], v[1], v[2], __int_as_float(side >= 0 ? DEAD : mat_id));
+  if (MIG && side >= 0) slot |= side << 30;  // carried across the projection in one register
+  else slot = -1;
+  // ---- plasticity (:165-178) ----
+  if (mat.kind == KIND_SNOW) {
+    const float ratio = plastic_project3(mat.sig_lo, mat.sig_hi, F);  // det(F) / det(F')
+    Jp = clampf(Jp * ratio, P.jp_min, P.jp_max);
+  } else if (mat.kind != KIND_JELLY) {
+    fluid_project(F);
+  }
+  out.xj[dst] = make_float4(x[0], x[1], x[2], Jp);
+#pragma unroll
+  for (int c = 0; c < 3; c++)
+#pragma unroll
+    for (int r = 0; r < 3; r++) out.F[c * 3 + r][dst] = F.d[c][r];
+  int id = 0;
+  if (RESORT || slot >= 0) id = A.s.id[i];
+  if (RESORT) out.id[dst] = id;
+  if (MIG && slot >= 0) {
+    // the record of an emigrant (layout of emigrate() in mpm_kernels.cu): x v F C Jp mat id pad; v and C are
+    // read back from where this thread stored them
+    const int sd = slot >> 30;
+    float *r = (sd == 0 ? A.mig.send_lo : A.mig.send_hi) + (size_t)(slot & 0x3fffffff) * MigRec<3>::WORDS;
+    const float4 vv = out.vm[dst];
+    float rec[MigRec<3>::WORDS];
+    rec[0] = x[0]; rec[1] = x[1]; rec[2] = x[2];
+    rec[3] = vv.x; rec[4] = vv.y; rec[5] = vv.z;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        rec[6 + c * 3 + k] = F.d[c][k];
+        rec[15 + c * 3 + k] = out.C[c * 3 + k][dst];
+      }
+    rec[24] = Jp;
+    rec[25] = __int_as_float(mat_id);
+    rec[26] = __int_as_float(id);
+    rec[27] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < MigRec<3>::WORDS / 4; k++)
+      reinterpret_cast<float4 *>(r)[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+  }
+}
+
+__device__ __forceinline__ void g2p3_report(const G2p3Args &A, float vmax) {
+  if (A.stats) {  // largest displacement of this substep in cells: feeds the re-sort interval (see engine)
+    const unsigned bits = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax * A.dt * A.P.inv_dx));
+    unsigned *slot = reinterpret_cast<unsigned *>(&A.stats[2]);
+    if ((threadIdx.x & 31) == 0 && bits > *reinterpret_cast<volatile unsigned *>(slot)) atomicMax(slot, bits);
+  }
+}
+
+// thread per particle, slots [first, n): the immigrant tail behind the binned range, and everything when
+// MPM_G2P3_TILE is off
 template <bool MIG, bool FLIP, bool RESORT>
 __global__ void __launch_bounds__(128, MPM_G2P3_FAST_MINB) k_g2p3(const __grid_constant__ G2p3Args A) {
-  const Params &P = A.P;
   long long n = A.n;
   if (MIG && A.dev_n && n > *A.dev_n) n = *A.dev_n;  // x-slab handles: exact extent on the device
   float vmax = 0.0f;
-  // Grid-stride loop with ONE prefetch: the position of a thread's next particle.  A particle's critical chain is two
-  // dependent memory latencies (position -> base cell -> 27 node loads); with the position already in registers only
-  // the node loads remain, and F / v / the next position are in flight beside them.
+  // optional grid-stride loop with ONE prefetch, the position of the thread's next particle (see MPM_G2P3_WAVES)
   const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = A.first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float4 xj_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -40,116 +162,77 @@ __global__ void __launch_bounds__(128, MPM_G2P3_FAST_MINB) k_g2p3(const __grid_c
     const float4 xj = xj_next;
     if (i + stride < n) xj_next = A.s.xj[i + stride];
     const float4 vm = A.s.vm[i];
-    const int mat_id = __float_as_int(vm.w);
-    if (!(MIG && mat_id == DEAD)) {  // slot of a particle that emigrated earlier: dropped by the re-sort
-      Mat<3> F;
+    if (MIG && __float_as_int(vm.w) == DEAD) continue;  // slot of a particle that emigrated earlier: dropped by the re-sort
+    Mat<3> F;
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) F.d[c][r] = A.s.F[c * 3 + r][i];
+    g2p3_particle<MIG, FLIP, RESORT, false>(A, i, xj, vm, F, nullptr, nullptr, 0, 0, 0, vmax);
+  }
+  g2p3_report(A, vmax);
+}
+
+// CTA per chunk of a bin: the 8^3 node velocities the bin's particles can touch are staged in shared memory ONCE
+// (coalesced, one memory latency per CTA); a particle's critical chain position -> base cell -> 27 node loads then
+// ends in shared memory, and the loads of the thread's next particle (position, material, F) are in flight while
+// the current one is computed.  The thread-per-particle kernel above was bound by exactly that chain: long-scoreboard
+// stalls 7.8 warps per issue at 39 % occupancy (profiles/r02_ncu_full_c5.md).
+template <bool MIG, bool FLIP, bool RESORT>
+__global__ void __launch_bounds__(128, MPM_G2P3_FAST_MINB) k_g2p3_tile(const __grid_constant__ G2p3Args A) {
+  __shared__ float4 tile[TILE_NODES];
+  __shared__ float4 tile_o[FLIP ? TILE_NODES : 1];
+  const Params &P = A.P;
+  const int tid = threadIdx.x;
+  const int4 work = A.chunks[blockIdx.x];
+  const int c0 = work.y, m = work.z;
+  // global node of tile node (0,0,0): bin origin minus the drift margin
+  const int tox = (work.w >> 20) * 4 + P.slab_lo - 1, toy = ((work.w >> 10) & 0x3ff) * 4 - 1, toz = (work.w & 0x3ff) * 4 - 1;
+  // first particle of this thread: in flight while the tile loads
+  float4 xj_n = make_float4(0.0f, 0.0f, 0.0f, 0.0f), vm_n = xj_n;
+  Mat<3> F_n;
+  if (tid < m) {
+    xj_n = A.s.xj[c0 + tid];
+    vm_n = A.s.vm[c0 + tid];
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int r = 0; r < 3; r++) F_n.d[c][r] = A.s.F[c * 3 + r][c0 + tid];
+  }
+  for (int t = tid; t < TN * TN * TN; t += 128) {
+    const int li = t >> 6, lj = (t >> 3) & 7, lk = t & 7;
+    const int gi = tox + li, gj = toy + lj, gk = toz + lk;
+    float4 g4 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), o4 = g4;
+    if (gi >= P.slab_lo && gi < P.slab_lo + P.ncol && gj >= 0 && gj < P.n1 && gk >= 0 && gk < P.n1) {
+      const long long node = ((long long)(gi - P.slab_lo) * P.n1 + gj) * P.n1 + gk;
+      g4 = __ldg(A.grid + node);
+      if (FLIP) o4 = __ldg(A.vold + node);
+    }
+    tile[(li * TN + lj) * TZ + lk] = g4;
+    if (FLIP) tile_o[(li * TN + lj) * TZ + lk] = o4;
+  }
+  __syncthreads();
+  float vmax = 0.0f;
+  for (int i = tid; i < m; i += 128) {
+    const float4 xj = xj_n, vm = vm_n;
+    const Mat<3> F = F_n;
+    if (i + 128 < m) {  // software pipeline: the next particle's loads go out before this one is computed
+      xj_n = A.s.xj[c0 + i + 128];
+      vm_n = A.s.vm[c0 + i + 128];
 #pragma unroll
       for (int c = 0; c < 3; c++)
 #pragma unroll
-        for (int r = 0; r < 3; r++) F.d[c][r] = A.s.F[c * 3 + r][i];
-      const SoA<3> &out = RESORT ? A.d : A.s;
-      long long dst = i;
-      if (RESORT) dst = (long long)A.new_start[A.key[i]] + A.rank[i];
-      float x[3] = {xj.x, xj.y, xj.z};
-      float Jp = xj.w;
-      const Material &mat = P.mat[material_index(P, mat_id)];
-      {
-        // ---- gather (:136-156), advect (:159), F update (:162) ----
-        Stencil<3> st = make_stencil<3>(x, P.inv_dx);
-        clamp_base<3>(P, st.base);  // G2P never flags (P2G did)
-        float v[3], dv[3] = {0.0f, 0.0f, 0.0f};
-        Mat<3> C;
-        gather3_fast(P, st, A.grid, A.vold, FLIP, v, C, dv);
-        const float s4 = 4 * P.inv_dx;  // the constant of :154, applied once
-#pragma unroll
-        for (int cc = 0; cc < 3; cc++)
-#pragma unroll
-          for (int r = 0; r < 3; r++) C.d[cc][r] = s4 * C.d[cc][r];
-        vmax = fmaxf(vmax, fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2]))));
-#pragma unroll
-        for (int k = 0; k < 3; k++) x[k] = x[k] + A.dt * v[k];
-        if (FLIP) {
-          const float a = P.alpha;
-          const float v_in[3] = {vm.x, vm.y, vm.z};
-#pragma unroll
-          for (int k = 0; k < 3; k++) v[k] = (1.0f - a) * v[k] + a * (v_in[k] + dv[k]);
-        }
-        F = mat_mul<3>(mat_add<3>(mat_diag<3>(1.0f), mat_scale<3>(A.dt, C)), F);
-        // ---- C and v are final: out they go ----
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-          for (int r = 0; r < 3; r++) out.C[c * 3 + r][dst] = C.d[c][r];
-        // x-slab runs: a particle whose NEW base column left the slab reserves its slot in that side's message
-        int side = -1, slot = 0;
-        if (MIG) {
-          const int nbx = max(0, min(base_coord(x[0], P.inv_dx), P.n_grid - 2));
-          if (A.mig.interior) {
-            if ((P.slab_lo > 0 && nbx < P.slab_lo + 2) || (P.slab_hi < P.n_grid && nbx + 4 > P.slab_hi))
-              atomicOr(A.status, STATUS_CFL);
-          } else {
-            side = nbx < P.slab_lo ? 0 : (nbx >= P.slab_hi ? 1 : -1);
-            if (side >= 0) {
-              slot = atomicAdd(&A.mig.count[side], 1);
-              if (slot >= A.mig.cap) {
-                atomicOr(A.status, STATUS_MIGRATION_OVERFLOW);  // stays here (and will be flagged out of slab)
-                side = -1;
-              }
-            }
-          }
-        }
-        out.vm[dst] = make_float4(v[0], v[1], v[2], __int_as_float(side >= 0 ? DEAD : mat_id));
-        if (MIG && side >= 0) slot |= side << 30;  // carried across the projection in one register
-        else slot = -1;
-        // ---- plasticity (:165-178) ----
-        if (mat.kind == KIND_SNOW) {
-          const float ratio = plastic_project3(mat.sig_lo, mat.sig_hi, F);  // det(F) / det(F')
-          Jp = clampf(Jp * ratio, P.jp_min, P.jp_max);
-        } else if (mat.kind != KIND_JELLY) {
-          fluid_project(F);
-        }
-        out.xj[dst] = make_float4(x[0], x[1], x[2], Jp);
-#pragma unroll
-        for (int c = 0; c < 3; c++)
-#pragma unroll
-          for (int r = 0; r < 3; r++) out.F[c * 3 + r][dst] = F.d[c][r];
-        int id = 0;
-        if (RESORT || slot >= 0) id = A.s.id[i];
-        if (RESORT) out.id[dst] = id;
-        if (MIG && slot >= 0) {
-          // the record of an emigrant (layout of emigrate() in mpm_kernels.cu): x v F C Jp mat id pad; v and C are
-          // read back from where this thread stored them
-          const int sd = slot >> 30;
-          float *r = (sd == 0 ? A.mig.send_lo : A.mig.send_hi) + (size_t)(slot & 0x3fffffff) * MigRec<3>::WORDS;
-          const float4 vv = out.vm[dst];
-          float rec[MigRec<3>::WORDS];
-          rec[0] = x[0]; rec[1] = x[1]; rec[2] = x[2];
-          rec[3] = vv.x; rec[4] = vv.y; rec[5] = vv.z;
-#pragma unroll
-          for (int c = 0; c < 3; c++)
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
-              rec[6 + c * 3 + k] = F.d[c][k];
-              rec[15 + c * 3 + k] = out.C[c * 3 + k][dst];
-            }
-          rec[24] = Jp;
-          rec[25] = __int_as_float(mat_id);
-          rec[26] = __int_as_float(id);
-          rec[27] = 0.0f;
-#pragma unroll
-          for (int k = 0; k < MigRec<3>::WORDS / 4; k++)
-            reinterpret_cast<float4 *>(r)[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
-        }
-      }
+        for (int r = 0; r < 3; r++) F_n.d[c][r] = A.s.F[c * 3 + r][c0 + i + 128];
     }
+    if (MIG && __float_as_int(vm.w) == DEAD) continue;
+    g2p3_particle<MIG, FLIP, RESORT, true>(A, (long long)c0 + i, xj, vm, F, tile, tile_o, tox, toy, toz, vmax);
   }
-  if (A.stats) {  // largest displacement of this substep in cells: feeds the re-sort interval (see engine)
-    const unsigned bits = __reduce_max_sync(0xffffffffu, __float_as_uint(vmax * A.dt * P.inv_dx));
-    unsigned *slot = reinterpret_cast<unsigned *>(&A.stats[2]);
-    if ((threadIdx.x & 31) == 0 && bits > *reinterpret_cast<volatile unsigned *>(slot)) atomicMax(slot, bits);
-  }
+  g2p3_report(A, vmax);
 }
 
+}  // namespace
+
+namespace {
 
 // ------------------------------------------------------------------------------------------------------------------
 // The fused 3D substep kernel: G2P of substep n and P2G of substep n+1 in one pass over the particles, one CTA per
@@ -495,6 +578,20 @@ void launch_g2p3(const G2p3Args &a, bool flip, bool mig, bool resort, cudaStream
     else      { if (resort) MPM_G3(false, false, true); else MPM_G3(false, false, false); }
   }
 #undef MPM_G3
+}
+
+// the binned range through the work list (a.chunks / a.n_chunks), one CTA per chunk
+void launch_g2p3_tile(const G2p3Args &a, bool flip, bool mig, bool resort, cudaStream_t st) {
+  if (a.n_chunks <= 0) return;
+#define MPM_G3T(F_, M_, R_) k_g2p3_tile<F_, M_, R_><<<a.n_chunks, 128, 0, st>>>(a)
+  if (mig) {
+    if (flip) { if (resort) MPM_G3T(true, true, true); else MPM_G3T(true, true, false); }
+    else      { if (resort) MPM_G3T(true, false, true); else MPM_G3T(true, false, false); }
+  } else {
+    if (flip) { if (resort) MPM_G3T(false, true, true); else MPM_G3T(false, true, false); }
+    else      { if (resort) MPM_G3T(false, false, true); else MPM_G3T(false, false, false); }
+  }
+#undef MPM_G3T
 }
 
 }  // namespace mpm
