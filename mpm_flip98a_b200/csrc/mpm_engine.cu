@@ -768,7 +768,8 @@ int mpm_handle::step_grid_g2p(float dt) {
     Phase ph(this, MPM_PHASE_GRID, 1);
     if (tiles_on()) {
       // update of this substep's grid and reset of the next P2G target in one launch, touched tiles only
-      launch_grid_tiles(P, dt, grid, vold, touched_g, grid_next, touched_n, tiles_x, tiles_y, stream);
+      launch_grid_tiles(P, dt, grid, vold, touched_g, grid_next, touched_n, tiles_x, tiles_y, stream, stats_dev,
+                        overlap ? (int)steps_since_sort + 1 : 0, status_dev);
       if (multi) {
         // the two tile columns next to each cut: ghost sums, migrating particles and the immigrant tail land there
         // through kernels that do not mark tiles themselves
@@ -867,7 +868,10 @@ int mpm_handle::step_grid_g2p(float dt) {
         const int c1 = part == 0 || part == 3 ? n_chunks : (part == 1 ? chunk_lo_end : chunk_hi_begin);
         x.chunks = sa.chunks + c0;
         x.n_chunks = c1 - c0;
-        launch_substep2d(x, flip, mg.enabled != 0, resort, st);
+        // the interior launch of the overlapped schedule runs the plain (single-GPU) variant: its chunks hold no dead
+        // slots (only boundary chunks lose particles, immigrants sit in the tail) and none of its particles can reach
+        // the cut -- guaranteed by the displacement guard in k_grid_tiles, not by a per-particle test
+        launch_substep2d(x, flip, mg.enabled != 0 && part != 2, resort, st);
       } else if (D == 2) {
         launch_g2p2g<2>(P, Gx, dt, dt, s2[cur], n_binned, bin_start, gp<2>(), grid_next, status_dev, stats_dev, mg, strict, st);
       } else {

@@ -57,8 +57,17 @@ __global__ void __launch_bounds__(256) k_grid_update(Params P, float dt, float4 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_grid_tiles(Params P, float dt, float4 *__restrict__ upd, float2 *__restrict__ vold,
                                                     const unsigned char *__restrict__ t_upd, float4 *__restrict__ clr,
-                                                    unsigned char *__restrict__ t_clr, int tiles_y) {
+                                                    unsigned char *__restrict__ t_clr, int tiles_y,
+                                                    const unsigned long long *__restrict__ stats, int guard_steps,
+                                                    int *__restrict__ status) {
   const int tx = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (guard_steps > 0 && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
+    // overlapped slab schedule: the interior launch runs WITHOUT the per-particle migration code; what makes that safe
+    // is checked here, once per substep: no particle can have travelled the >= 14 cells between an interior bin and the
+    // slab cut while (substeps since the re-sort + 2) x (largest per-substep displacement measured since) <= 8 cells
+    const float d = __uint_as_float((unsigned)(stats[2] & 0xffffffffull));
+    if (d * (float)(guard_steps + 2) > 8.0f) atomicOr(status, STATUS_CFL);
+  }
   const int i = tx * 8 + w;  // local node column
   const int j0 = blockIdx.y * 128;
   const bool flip = P.alpha != 0.0f;
@@ -92,9 +101,10 @@ __global__ void __launch_bounds__(256) k_grid_tiles(Params P, float dt, float4 *
   }
 }
 void launch_grid_tiles(const Params &P, float dt, float4 *upd, void *vold, const unsigned char *t_upd, float4 *clr,
-                       unsigned char *t_clr, int tiles_x, int tiles_y, cudaStream_t st) {
+                       unsigned char *t_clr, int tiles_x, int tiles_y, cudaStream_t st, const unsigned long long *stats,
+                       int guard_steps, int *status) {
   dim3 grid((unsigned)tiles_x, (unsigned)((P.n1 + 127) / 128));
-  k_grid_tiles<<<grid, 256, 0, st>>>(P, dt, upd, (float2 *)vold, t_upd, clr, t_clr, tiles_y);
+  k_grid_tiles<<<grid, 256, 0, st>>>(P, dt, upd, (float2 *)vold, t_upd, clr, t_clr, tiles_y, stats, guard_steps, status);
 }
 
 template <int D>

@@ -44,8 +44,11 @@ void launch_slab_counters(int *ext, const int *add_a, const int *add_b, const in
 template <int D>
 void launch_grid_update(const Params &P, float dt, GridPtrs<D> g, cudaStream_t st);
 // 2D: update `upd` and reset `clr` on the tiles (8x8 nodes) their byte maps mark; see k_grid_tiles
+// guard_steps > 0 (overlapped slab schedule): flags STATUS_CFL when (guard_steps + 2) x the largest per-substep
+// displacement in stats[2] exceeds 8 cells -- the condition under which the interior launch may skip the migration code
 void launch_grid_tiles(const Params &P, float dt, float4 *upd, void *vold, const unsigned char *t_upd, float4 *clr,
-                       unsigned char *t_clr, int tiles_x, int tiles_y, cudaStream_t st);
+                       unsigned char *t_clr, int tiles_x, int tiles_y, cudaStream_t st,
+                       const unsigned long long *stats = nullptr, int guard_steps = 0, int *status = nullptr);
 
 // ---- binned path: one CTA per bin, in-CTA cell sort + register accumulation (see mpm_kernels.cu) --
 template <int D>

@@ -22,6 +22,34 @@ namespace {
 #ifndef MPM_G2P3_FAST_MINB
 #define MPM_G2P3_FAST_MINB 7
 #endif
+#ifndef MPM_G2P3_WAVES
+#define MPM_G2P3_WAVES 0  // > 0: cap the grid at this many CTAs per resident slot, the rest is the grid-stride loop with the
+                          // position prefetch.  Measured on c5: 4 waves 1.60 ms, uncapped (one particle per thread) 1.52 ms
+#endif
+
+// x-slab runs: the record of an emigrant (layout of emigrate() in mpm_kernels.cu: x v F C Jp mat id pad), read back from
+// where the thread stored the particle's new state a moment ago (`out`, slot dst).  Out of line and fed with four
+// integers only: inlined, the 28-word record of this rare branch raised the register pressure of EVERY particle (the
+// MIG variants of the 3D G2P spilled 164 bytes and ran 28 % slower than the single-GPU variant on the first 2-GPU run).
+__device__ __noinline__ void pack_emigrant3(const SoA<3> &out, long long dst, int slot_side, int mat_id, int id,
+                                            float *send_lo, float *send_hi) {
+  const int sd = slot_side >> 30;
+  float4 *r = reinterpret_cast<float4 *>((sd == 0 ? send_lo : send_hi) + (size_t)(slot_side & 0x3fffffff) * MigRec<3>::WORDS);
+  const float4 xj = out.xj[dst], vv = out.vm[dst];
+  float F[9], C[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) {
+    F[k] = out.F[k][dst];
+    C[k] = out.C[k][dst];
+  }
+  r[0] = make_float4(xj.x, xj.y, xj.z, vv.x);
+  r[1] = make_float4(vv.y, vv.z, F[0], F[1]);
+  r[2] = make_float4(F[2], F[3], F[4], F[5]);
+  r[3] = make_float4(F[6], F[7], F[8], C[0]);
+  r[4] = make_float4(C[1], C[2], C[3], C[4]);
+  r[5] = make_float4(C[5], C[6], C[7], C[8]);
+  r[6] = make_float4(xj.w, __int_as_float(mat_id), __int_as_float(id), 0.0f);
+}
 
 // tile of node velocities a CTA of k_g2p3_tile stages in shared memory: the bin's 4^3 base cells + 1-cell drift margin
 // + stencil reach = 8 nodes per axis; z rows padded to 9 float4 (144 B) so that neighbouring y rows do not share banks
@@ -112,30 +140,7 @@ __device__ __forceinline__ void g2p3_particle(const G2p3Args &A, long long i, fl
   int id = 0;
   if (RESORT || slot >= 0) id = A.s.id[i];
   if (RESORT) out.id[dst] = id;
-  if (MIG && slot >= 0) {
-    // the record of an emigrant (layout of emigrate() in mpm_kernels.cu): x v F C Jp mat id pad; v and C are
-    // read back from where this thread stored them
-    const int sd = slot >> 30;
-    float *r = (sd == 0 ? A.mig.send_lo : A.mig.send_hi) + (size_t)(slot & 0x3fffffff) * MigRec<3>::WORDS;
-    const float4 vv = out.vm[dst];
-    float rec[MigRec<3>::WORDS];
-    rec[0] = x[0]; rec[1] = x[1]; rec[2] = x[2];
-    rec[3] = vv.x; rec[4] = vv.y; rec[5] = vv.z;
-#pragma unroll
-    for (int c = 0; c < 3; c++)
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        rec[6 + c * 3 + k] = F.d[c][k];
-        rec[15 + c * 3 + k] = out.C[c * 3 + k][dst];
-      }
-    rec[24] = Jp;
-    rec[25] = __int_as_float(mat_id);
-    rec[26] = __int_as_float(id);
-    rec[27] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < MigRec<3>::WORDS / 4; k++)
-      reinterpret_cast<float4 *>(r)[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
-  }
+  if (MIG && slot >= 0) pack_emigrant3(out, dst, slot, mat_id, id, A.mig.send_lo, A.mig.send_hi);
 }
 
 __device__ __forceinline__ void g2p3_report(const G2p3Args &A, float vmax) {
@@ -153,22 +158,34 @@ __global__ void __launch_bounds__(128, MPM_G2P3_FAST_MINB) k_g2p3(const __grid_c
   long long n = A.n;
   if (MIG && A.dev_n && n > *A.dev_n) n = *A.dev_n;  // x-slab handles: exact extent on the device
   float vmax = 0.0f;
-  // optional grid-stride loop with ONE prefetch, the position of the thread's next particle (see MPM_G2P3_WAVES)
-  const long long stride = (long long)gridDim.x * blockDim.x;
   long long i = A.first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  float4 xj_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  if (i < n) xj_next = A.s.xj[i];
-  for (; i < n; i += stride) {
-    const float4 xj = xj_next;
-    if (i + stride < n) xj_next = A.s.xj[i + stride];
-    const float4 vm = A.s.vm[i];
-    if (MIG && __float_as_int(vm.w) == DEAD) continue;  // slot of a particle that emigrated earlier: dropped by the re-sort
-    Mat<3> F;
+  if (MPM_G2P3_WAVES > 0) {
+    // grid-stride loop with ONE prefetch, the position of the thread's next particle (see MPM_G2P3_WAVES)
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    float4 xj_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (i < n) xj_next = A.s.xj[i];
+    for (; i < n; i += stride) {
+      const float4 xj = xj_next;
+      if (i + stride < n) xj_next = A.s.xj[i + stride];
+      const float4 vm = A.s.vm[i];
+      if (MIG && __float_as_int(vm.w) == DEAD) continue;  // slot of a particle that emigrated earlier
+      Mat<3> F;
 #pragma unroll
-    for (int c = 0; c < 3; c++)
+      for (int c = 0; c < 3; c++)
 #pragma unroll
-      for (int r = 0; r < 3; r++) F.d[c][r] = A.s.F[c * 3 + r][i];
-    g2p3_particle<MIG, FLIP, RESORT, false>(A, i, xj, vm, F, nullptr, nullptr, 0, 0, 0, vmax);
+        for (int r = 0; r < 3; r++) F.d[c][r] = A.s.F[c * 3 + r][i];
+      g2p3_particle<MIG, FLIP, RESORT, false>(A, i, xj, vm, F, nullptr, nullptr, 0, 0, 0, vmax);
+    }
+  } else if (i < n) {
+    const float4 xj = A.s.xj[i], vm = A.s.vm[i];
+    if (!(MIG && __float_as_int(vm.w) == DEAD)) {  // slot of a particle that emigrated earlier: dropped by the re-sort
+      Mat<3> F;
+#pragma unroll
+      for (int c = 0; c < 3; c++)
+#pragma unroll
+        for (int r = 0; r < 3; r++) F.d[c][r] = A.s.F[c * 3 + r][i];
+      g2p3_particle<MIG, FLIP, RESORT, false>(A, i, xj, vm, F, nullptr, nullptr, 0, 0, 0, vmax);
+    }
   }
   g2p3_report(A, vmax);
 }
@@ -372,27 +389,7 @@ __global__ void __launch_bounds__(NT3, MPM_SUBSTEP3D_MINB) k_substep3d(const __g
     if (RESORT || gone_slot >= 0) id = A.s.id[slot_i];
     if (RESORT) out.id[dst] = id;
     if (MIG && gone_slot >= 0) {
-      // the record of an emigrant (layout of emigrate() in mpm_kernels.cu); v and C read back from this thread's stores
-      const int sd = gone_slot >> 30;
-      float *r = (sd == 0 ? A.mig.send_lo : A.mig.send_hi) + (size_t)(gone_slot & 0x3fffffff) * MigRec<3>::WORDS;
-      const float4 vv = out.vm[dst];
-      float rec[MigRec<3>::WORDS];
-      rec[0] = x[0]; rec[1] = x[1]; rec[2] = x[2];
-      rec[3] = vv.x; rec[4] = vv.y; rec[5] = vv.z;
-#pragma unroll
-      for (int c = 0; c < 3; c++)
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          rec[6 + c * 3 + k] = F.d[c][k];
-          rec[15 + c * 3 + k] = out.C[c * 3 + k][dst];
-        }
-      rec[24] = Jp;
-      rec[25] = __int_as_float(mat_id);
-      rec[26] = __int_as_float(id);
-      rec[27] = 0.0f;
-#pragma unroll
-      for (int k = 0; k < MigRec<3>::WORDS / 4; k++)
-        reinterpret_cast<float4 *>(r)[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+      pack_emigrant3(out, dst, gone_slot, mat_id, id, A.mig.send_lo, A.mig.send_hi);
       cr[i] = 0xffffffffu;  // no P2G here: the receiving handle scatters it when it arrives
       continue;
     }
@@ -551,10 +548,6 @@ __global__ void __launch_bounds__(NT3, MPM_SUBSTEP3D_MINB) k_substep3d(const __g
 
 }  // namespace
 
-#ifndef MPM_G2P3_WAVES
-#define MPM_G2P3_WAVES 0  // > 0: cap the grid at this many CTAs per resident slot, the rest is the grid-stride loop with the
-                          // position prefetch.  Measured on c5: 4 waves 1.60 ms, uncapped (one particle per thread) 1.52 ms
-#endif
 void launch_g2p3(const G2p3Args &a, bool flip, bool mig, bool resort, cudaStream_t st) {
   if (a.n - a.first <= 0) return;
   unsigned blocks = (unsigned)((a.n - a.first + 127) / 128);

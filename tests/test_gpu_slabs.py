@@ -204,3 +204,30 @@ def test_overlapped_schedule_3d(oracle):
     assert sa == [0, 0] and sb_ == [0, 0] and sum(ca) == len(p) and sum(cb) == len(p)
     assert (parallel.owner_of(warm[:, 0], n, slabs) != parallel.owner_of(a[:, 0], n, slabs)).sum() > 100
     assert rel_l2(a[:, 0:3], b[:, 0:3]) <= 1e-5 and rel_l2(a[:, 3:6], b[:, 3:6]) <= 1e-3
+
+
+def test_overlap_guard_flags_a_too_long_resort_interval():
+    """The interior launch of the overlapped schedule skips the migration code; what licenses that -- no particle can
+    have travelled from an interior bin to the slab cut since the last re-sort -- is checked on the device every substep
+    from the measured displacements.  A fixed, far too long re-sort interval with fast particles must raise MPM_E_CFL."""
+    from mpm_flip98a_b200.engine import FLAG_OVERLAP
+    n = 512
+    dt, vol = scenes.scaled_constants(n)
+    p = scenes.three_blocks_2d(n, per_side=2)
+    p[:, 2] = 30.0  # 0.24 cells per substep: the guard trips once (substeps since the re-sort + 2) x 0.24 > 8
+    ranks, ex, slabs = parallel.make_local_cluster(mpm.Engine, p, 2, n, 2, dt=dt, vol_p=vol, flags=FLAG_OVERLAP,
+                                                   rebin_every=400, shared_stream=True)
+    parallel.step_local(ranks, ex, 45, settle=False)
+    status = [r.e.poll_status() for r in ranks]
+    for r in ranks:
+        r.e.close()
+    assert -5 in status, status  # MPM_E_CFL
+    # ... and the adaptive interval keeps the same run clean
+    ranks, ex, slabs = parallel.make_local_cluster(mpm.Engine, p, 2, n, 2, dt=dt, vol_p=vol, flags=FLAG_OVERLAP,
+                                                   shared_stream=True)
+    parallel.step_local(ranks, ex, 45)
+    status = [r.e.poll_status() for r in ranks]
+    n_live = sum(r.e.count for r in ranks)
+    for r in ranks:
+        r.e.close()
+    assert status == [0, 0] and n_live == len(p), (status, n_live)
