@@ -985,7 +985,7 @@ int mpm_handle::step_grid_g2p(float dt) {
       ga.chunks = chunks_buf[bs];
       ga.n_chunks = n_chunks;
 #ifndef MPM_G2P3_TILE
-#define MPM_G2P3_TILE 1
+#define MPM_G2P3_TILE 0  // measured on c5 (B200): tile variant 1.83-2.23 ms at 5-7 CTAs/SM vs 1.48 ms thread-per-particle
 #endif
       if (MPM_G2P3_TILE && chunk_offs) {
         // binned range: CTA per chunk with the node tile in shared memory; immigrant tail: thread per particle

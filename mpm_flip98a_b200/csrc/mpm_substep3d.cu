@@ -190,6 +190,9 @@ __global__ void __launch_bounds__(128, MPM_G2P3_FAST_MINB) k_g2p3(const __grid_c
   g2p3_report(A, vmax);
 }
 
+// [opt-in at build time, -DMPM_G2P3_TILE=1: measured SLOWER than k_g2p3 on B200 -- 1.83 ms (5 CTAs/SM) ... 2.23 ms (6)
+// against 1.48 ms on the 256^3 scene: the 14 prefetch registers spill at 72 and 27 LDS.128 per particle load the L1
+// pipe as much as the read-only-path gather did]
 // CTA per chunk of a bin: the 8^3 node velocities the bin's particles can touch are staged in shared memory ONCE
 // (coalesced, one memory latency per CTA); a particle's critical chain position -> base cell -> 27 node loads then
 // ends in shared memory, and the loads of the thread's next particle (position, material, F) are in flight while
