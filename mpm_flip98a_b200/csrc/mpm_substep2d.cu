@@ -17,6 +17,8 @@
 //   * records split into two float4 planes (half the shared-memory bank conflicts of 32-byte records);
 //   * a work list entry per chunk, read with ONE load (the round-1 chain active bin -> bin range -> particles cost
 //     three dependent memory latencies at every CTA start), dense bins spread over several CTAs.
+// (Tried and removed: persistent CTAs walking the work list with a prefetch of the next chunk's first particles --
+// 6.45 vs 6.15 ms on c4 at equal clocks; even compiled out, the loop structure cost 4 % more instructions.)
 // RESORT = true additionally performs the storage re-sort on the fly: each particle's new state is written
 // to its slot in the OTHER storage buffer (slot = new bin start + rank, both computed from the positions
 // before this substep by k_count_rank), so a re-sort costs one 12-byte pass instead of a radix sort plus a
@@ -131,19 +133,11 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
   const int x_lo = P.slab_lo, x_hi = min(P.slab_hi, P.n_grid - 1) - 1;  // clamp range of base x (clamp_base)
   unsigned n_fallback = 0;
   float vmax = 0.0f;  // fastest particle of this thread (max norm): feeds the re-sort interval (CFL), see engine
-  // Persistent CTAs: the grid is one CTA per resident slot and each CTA walks the work list with that stride.  The
-  // descriptor of a CTA's NEXT chunk and the loads of that chunk's first particles are issued before phase 2 of the
-  // current one, so a chunk no longer starts with two dependent memory latencies (descriptor -> particles) during
-  // which its warps only wait: 17 % of the round-2 kernel's stall samples sat on those first-use instructions.
-  int4 work = A.chunks[blockIdx.x];  // one load: no bin -> range -> particle chain
-  PS nxt;
-  if (tid < work.z) load_g2p2(A.s, work.y + tid, nxt, FLIP);
-  for (int w = blockIdx.x; w < A.n_chunks; w += gridDim.x) {
-    const int c0 = work.y, m = work.z;
-    const int ox = (work.w >> 16) * B + P.slab_lo - M, oy = (work.w & 0xffff) * B - M;  // global cell of local cell 0
-    const int bin_xy = work.w;
-    const bool more = w + (int)gridDim.x < A.n_chunks;
-    if (more) work = A.chunks[w + gridDim.x];  // consumed after phase 1
+  const int4 work = A.chunks[blockIdx.x];  // one load: no bin -> range -> particle chain at CTA start
+  const int c0 = work.y, m = work.z;
+  const int ox = (work.w >> 16) * B + P.slab_lo - M, oy = (work.w & 0xffff) * B - M;  // global cell of local cell 0
+  const int bin_xy = work.w;
+  {
     if (tid < NC) cnt[tid] = 0;
     if (tid < 9) {
       // this CTA's REDs land on the nodes of cells [ox, ox+L) x [oy, oy+L): the 3x3 tiles around the bin's own
@@ -152,6 +146,8 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
     }
     __syncthreads();
     // ---------------- phase 1: thread per particle (G2P of this substep, P2G record of the next) -------------
+    PS nxt;
+    if (tid < m) load_g2p2(A.s, c0 + tid, nxt, FLIP);
     for (int i = tid; i < m; i += NT) {
       PS p = nxt;  // loads issued one iteration ago; the next particle's go out now (software pipeline)
       if (i + NT < m) load_g2p2(A.s, c0 + i + NT, nxt, FLIP);
@@ -248,7 +244,6 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
         }
       }
     }
-    if (more && tid < work.z) load_g2p2(A.s, work.y + tid, nxt, FLIP);  // first particles of the next chunk: in flight during the scans and phase 2
     __syncthreads();
     // ---------------- scans on all four warps: record starts and work items per cell ----------------
     {
@@ -334,7 +329,6 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
         atomicAdd(gp + a * n1 + 2, make_float4(acc[a][2].x, acc[a][2].y, m2[a], 0.0f));
       }
     }
-    __syncthreads();  // shared memory is reused by the next chunk
   }
   if (A.stats) {
     if (n_fallback) {
@@ -351,26 +345,9 @@ __global__ void __launch_bounds__(NT, MPM_SUBSTEP2D_MINB) k_substep2d(const __gr
 
 int substep2d_chunk_capacity() { return CAP; }
 
-#ifndef MPM_SUBSTEP2D_PERSISTENT
-#define MPM_SUBSTEP2D_PERSISTENT 0
-#endif
 void launch_substep2d(const Substep2dArgs &a, bool flip, bool mig, bool resort, cudaStream_t st) {
-  if (a.n_chunks <= 0) return;
-  int grid = a.n_chunks;
-  if (MPM_SUBSTEP2D_PERSISTENT) {
-    // one CTA per resident slot (SMs x CTAs per SM at the kernel's launch bounds)
-    static int slots[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64) {
-      if (!slots[dev]) {
-        int sms = 148;
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        slots[dev] = sms * MPM_SUBSTEP2D_MINB;
-      }
-      if (grid > slots[dev]) grid = slots[dev];
-    }
-  }
+  const int grid = a.n_chunks;
+  if (grid <= 0) return;
 #define MPM_S2D(F_, M_, R_) k_substep2d<F_, M_, R_><<<grid, NT, 0, st>>>(a)
   if (flip) {
     if (mig) { if (resort) MPM_S2D(true, true, true); else MPM_S2D(true, true, false); }

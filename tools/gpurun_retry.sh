@@ -1,7 +1,7 @@
 #!/bin/bash
 # tools/gpurun_retry.sh <out-file> <gpurun args...>: retries while the pod answers "busy" (exit 3)
 out=$1; shift
-for k in 1 2 3 4 5 6 7 8 9 10; do
+for k in $(seq 1 40); do
   /usr/local/graft/bin/gpurun "$@" > "$out" 2>&1
   rc=$?
   [ $rc -ne 3 ] && exit $rc
