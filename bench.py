@@ -604,7 +604,7 @@ def run_slabs(args, rank, world, local):
 
     with torch.cuda.stream(stream):
         balance = {"passes": 0, "cost_ms_per_rank": None, "imbalance_max_over_mean": None}
-        for attempt in range(3):
+        for attempt in range(2):  # at most ONE rebalancing pass (a pass regenerates and re-warms the scene: ~1.5 min at c4)
             host, ids, n_local, n_total, cap, eng, up, r, ex = setup(slabs)
             # calibration: each rank's device time per substep in the warm, moving state that will be timed
             parallel.step_dist(r, ex, args.warm_substeps, settle=False)
@@ -619,7 +619,7 @@ def run_slabs(args, rank, world, local):
             costs = [float(c) for c in costs]
             imb = max(costs) / (sum(costs) / world)
             balance.update(cost_ms_per_rank=[round(c, 4) for c in costs], imbalance_max_over_mean=round(imb, 4))
-            if imb <= 1.015 or attempt == 2 or args.no_rebalance:
+            if imb <= 1.015 or attempt == 1 or args.no_rebalance:
                 break
             new = rebalanced_cuts(slabs, costs, n_grid, edge, x_range)
             if new == slabs:
