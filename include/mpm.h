@@ -106,7 +106,8 @@ typedef struct mpm_config {
                          0 = engine default: 32 on the naive path, adaptive 2..512 on the binned path
                          (0.75 cells / the largest per-substep displacement the kernels measure) */
   int mig_records;    /* x-slab handles: emigrant records per message (must be the same on every handle of a
-                         decomposition); 0 = engine default, 2 x the nodes of a cut clamped to [4096, 262144] */
+                         decomposition); 0 = engine default: 2 x the nodes of a cut (2D) / half the nodes of a cut (3D),
+                         clamped to [4096, 262144] */
   int reserved[5];
 } mpm_config;
 

@@ -390,7 +390,9 @@ int mpm_handle::init() {
     // K = records per message.  Every handle of a decomposition must arrive at the same number (the messages have a
     // fixed size), so it depends on the GLOBAL grid only: twice the nodes of a cut (a column / plane of cells at
     // ~8-16 particles per cell times a CFL number <= 0.1-0.25), unless mpm_config.mig_records says otherwise
-    long long K = cfg.mig_records > 0 ? cfg.mig_records : halo_nodes();
+    // (3D: a quarter of that -- a plane of 8 particles per cell at a CFL number of 0.05 sends ~0.12 n^2 records, the two
+    // planes hold 2 n^2 nodes; the full count made the 3D message 38 MB at n = 512, most of it never filled)
+    long long K = cfg.mig_records > 0 ? cfg.mig_records : (D == 3 ? halo_nodes() / 4 : halo_nodes());
     if (cfg.mig_records <= 0) {
       if (K < 4096) K = 4096;
       if (K > (1 << 18)) K = 1 << 18;
