@@ -80,13 +80,30 @@ def progressBar(t, total, width=40, stream=sys.stdout):
     stream.flush()
 
 
+def write_frame(path, x, res=512, background=0x112F41, colour=0x068587):
+    """One frame of the "mov" directory: the particles splatted as single pixels into a res x res binary PPM
+    (background = the colour exec.py:14 gives its ti.GUI; y up like the GUI).  Headless stand-in for gui.show(file)."""
+    img = np.empty((res, res, 3), np.uint8)
+    img[:] = [(background >> 16) & 255, (background >> 8) & 255, background & 255]
+    ix = np.clip((x[:, 0] * res).astype(np.int64), 0, res - 1)
+    iy = np.clip(((1.0 - x[:, 1]) * res).astype(np.int64), 0, res - 1)
+    img[iy, ix] = [(colour >> 16) & 255, (colour >> 8) & 255, colour & 255]
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (res, res))
+        f.write(img.tobytes())
+    return path
+
+
 def post_process(numParticles, gui, vtkpath, filepath, num_substeps, count):
-    """exec.py:29 -- reads the particles back and writes one legacy-VTK point cloud (x, v, J = det F).
-    `gui` is accepted for signature compatibility and ignored (headless)."""
+    """exec.py:29 -- reads the particles back and writes one legacy-VTK point cloud (x, v, J = det F) into `vtkpath`
+    and one frame of the movie (PPM point splat) into `filepath`.  `gui` is accepted for signature compatibility
+    and ignored (headless: taichi's GUI is not available here)."""
     p = _state["engine"].read()[:numParticles]
     n = len(p)
     frame = _state["frame"]
     _state["frame"] += 1
+    if filepath:
+        write_frame(os.path.join(filepath, "frame_%06d.ppm" % frame), p[:, 0:2])
     name = os.path.join(vtkpath, "particles_%06d.vtk" % frame)
     J = p[:, 4] * p[:, 7] - p[:, 5] * p[:, 6]
     with open(name, "w") as f:

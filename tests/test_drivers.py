@@ -79,6 +79,10 @@ def test_exec_shim_runs_the_reference_loop(tmp_path, monkeypatch):
     assert "POINTS 8450 float" in text and "VECTORS velocity" in text  # 65 x 130 particles, config.py:30-32
     p = fc._state["engine"].read()
     assert np.isfinite(p).all() and p[:, 3].mean() < 0  # the column falls
+    frames = sorted(os.listdir(filepath))  # the "mov" directory of exec.py:16,29 (.gitignore:3): one PPM per frame
+    assert frames == ["frame_000000.ppm", "frame_000001.ppm"]
+    raw = open(os.path.join(filepath, frames[-1]), "rb").read()
+    assert raw.startswith(b"P6\n512 512\n255\n") and len(raw) == 15 + 512 * 512 * 3
 
 
 def test_checkpoint_format_roundtrip_cpu(tmp_path):
@@ -137,3 +141,16 @@ def test_cpp_driver_on_several_slabs(tmp_path, shipped):
     fw, fg = fields(want, 2), fields(p, 2)
     assert rel_l2(fg["x"], fw["x"]) < 1e-4 and rel_l2(fg["v"], fw["v"]) < 2e-2
     assert np.abs(p[:, 0:2].mean(0) - want[:, 0:2].mean(0)).max() < 1e-5
+
+
+def test_exec_shim_frame_writer_cpu(tmp_path):
+    """the movie frame of exec.py's "mov" directory: a binary PPM point splat, y up (no GPU involved)"""
+    from mpm_flip98a_b200 import exec_shim as fc
+    x = np.array([[0.25, 0.75], [0.999, 0.001]], np.float32)
+    path = fc.write_frame(str(tmp_path / "f.ppm"), x, res=64)
+    raw = open(path, "rb").read()
+    hdr = b"P6\n64 64\n255\n"
+    assert raw.startswith(hdr) and len(raw) == len(hdr) + 64 * 64 * 3
+    img = np.frombuffer(raw[len(hdr):], np.uint8).reshape(64, 64, 3)
+    assert tuple(img[16, 16]) == (0x06, 0x85, 0x87) and tuple(img[63, 63]) == (0x06, 0x85, 0x87)  # row = (1 - y) * res
+    assert tuple(img[0, 0]) == (0x11, 0x2F, 0x41)  # background of exec.py:14
