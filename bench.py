@@ -557,7 +557,7 @@ def run_slabs(args, rank, world, local):
     x_range = (0.05, 0.95) if args.workload in ("c4", "c5") else (0.05, 0.52)
     dt, vol = scenes.scaled_constants(n_grid, dim)
     dev = "cuda:%d" % local
-    overlap = dim == 2 and not args.no_overlap and not args.naive and not args.no_fuse
+    overlap = not args.no_overlap and not args.naive and (dim == 3 or not args.no_fuse)
     # with the overlapped schedule the engine's interior launch runs on a lowest-priority side stream; the main stream
     # (boundary bins, exchange helpers) and NCCL's own stream (TORCH_NCCL_HIGH_PRIORITY, set in __main__) outrank it
     stream = torch.cuda.Stream(priority=-1) if overlap else torch.cuda.Stream()

@@ -64,6 +64,7 @@ struct mpm_handle {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_ready = nullptr, ev_side_done = nullptr;
   int act_lo_end = 0, act_hi_begin = 0;
+  long long slot_lo_end = 0, slot_hi_begin = 0;  // storage slots of the boundary-lo bins | interior | boundary-hi bins
   void join_side() {  // everything issued on the main stream after this sees the side stream's work
     if (side_busy) {
       cudaStreamWaitEvent(stream, ev_side_done, 0);
@@ -455,7 +456,7 @@ int mpm_handle::init() {
       if ((rc = dalloc(&chunks_buf[b], (size_t)chunks_cap))) return rc;
     if ((rc = dalloc(&chunk_offs, (size_t)G.n_bins + 4))) return rc;
   }
-  overlap = fused && multi && (cfg.flags & MPM_FLAG_OVERLAP);
+  overlap = (fused || fast3d()) && multi && (cfg.flags & MPM_FLAG_OVERLAP);
   if (overlap) {
     {
       // lowest priority: when SM slots free up, boundary kernels (main stream) and the caller's NCCL kernels are
@@ -587,6 +588,9 @@ int mpm_handle::begin_resort() {
       MPM_CUDA(cudaMemcpyAsync(&resort_host[5], chunk_offs + lo_bin, 4, cudaMemcpyDeviceToHost, stream));
       MPM_CUDA(cudaMemcpyAsync(&resort_host[6], chunk_offs + hi_bin, 4, cudaMemcpyDeviceToHost, stream));
     }
+    // ... and so are their storage slots (the storage is sorted by bin): first slot of the interior, of boundary-hi
+    MPM_CUDA(cudaMemcpyAsync(&resort_host[7], ns + lo_bin, 4, cudaMemcpyDeviceToHost, stream));
+    MPM_CUDA(cudaMemcpyAsync(&resort_host[8], ns + hi_bin, 4, cudaMemcpyDeviceToHost, stream));
   }
   MPM_CUDA(cudaEventRecord(resort_ev, stream));
   resort_pending = true;
@@ -607,9 +611,13 @@ int mpm_handle::end_resort() {
   n_binned = n;
   act_lo_end = 0;
   act_hi_begin = G.n_active;
+  slot_lo_end = 0;
+  slot_hi_begin = n;
   if (overlap) {
     act_lo_end = resort_host[2];
     act_hi_begin = resort_host[3] > act_lo_end ? resort_host[3] : act_lo_end;
+    slot_lo_end = resort_host[7];
+    slot_hi_begin = resort_host[8] > slot_lo_end ? resort_host[8] : slot_lo_end;
   }
   if (chunk_offs) {
     n_chunks = resort_host[4];
@@ -960,6 +968,7 @@ int mpm_handle::step_grid_g2p(float dt) {
     // the kernel is the consumer, second half after it has been enqueued
     const bool fast3 = fast3d();
     const bool resort3 = fast3 && resort_due && n > 0;
+    bool p2g_overlapped = false;  // the overlapped 3D schedule below has already launched the next P2G
     if (resort3) {
       fused_resort_now = true;
       int rc = rebin_storage();
@@ -994,6 +1003,55 @@ int mpm_handle::step_grid_g2p(float dt) {
         launch_g2p3_tile(ga, P.alpha != 0.0f, mig.enabled != 0, resort3, stream);
         ga.first = n_binned;
       }
+      // Overlapped two-kernel schedule (MPM_FLAG_OVERLAP, no re-sort in this substep): G2P and the next P2G of the two bin
+      // columns next to each cut (a prefix and a suffix of the bin-sorted storage, plus the immigrant tail) run first on
+      // the main stream -- their emigrants and shared node planes are what the caller exchanges next -- while G2P + P2G of
+      // the interior follow on the low-priority side stream.  An interior particle can neither emigrate nor touch a
+      // shared plane: checked per particle by the kernel (mig.interior), flagged as MPM_E_CFL.
+      const bool ov3 = overlap && !resort3 && n > 0 && act_hi_begin > act_lo_end && slot_hi_begin > slot_lo_end;
+      if (ov3) {
+        const bool flip3 = P.alpha != 0.0f;
+        const bool strict_p2g = false;  // fast3d() excludes MPM_FLAG_STRICT
+        GridPtrs<3> gn = gp<3>();
+        gn.g = grid_next;
+        MPM_CUDA(cudaEventRecord(ev_ready, stream));  // grid updated, next grid cleared
+        {
+          Phase phb(this, MPM_PHASE_MIGRATE, 5);
+          G2p3Args gb = ga;
+          gb.first = 0;
+          gb.n = slot_lo_end;
+          launch_g2p3(gb, flip3, true, false, stream);
+          gb.first = slot_hi_begin;
+          gb.n = n;  // boundary-hi bins and the immigrant tail
+          launch_g2p3(gb, flip3, true, false, stream);
+          BinGeom Gb = G;
+          Gb.n_active = act_lo_end;
+          if (Gb.n_active > 0)
+            launch_p2g_cells<3>(P, Gb, dt, s3[cur], n_binned, bin_start, gn, status_dev, stats_dev, strict_p2g, stream);
+          Gb.active = G.active + act_hi_begin;
+          Gb.n_active = G.n_active - act_hi_begin;
+          if (Gb.n_active > 0)
+            launch_p2g_cells<3>(P, Gb, dt, s3[cur], n_binned, bin_start, gn, status_dev, stats_dev, strict_p2g, stream);
+          launch_p2g_naive<3>(P, dt, s3[cur], n_binned, n, gn, status_dev, stream, dev_ext);
+        }
+        MPM_CUDA(cudaStreamWaitEvent(side, ev_ready, 0));
+        {
+          Phase phs(this, MPM_PHASE_G2P, 2, side);
+          G2p3Args gi = ga;
+          gi.first = slot_lo_end;
+          gi.n = slot_hi_begin;
+          gi.dev_n = nullptr;  // the range lies inside the binned storage
+          gi.mig.interior = 1;
+          launch_g2p3(gi, flip3, true, false, side);
+          BinGeom Gi = G;
+          Gi.active = G.active + act_lo_end;
+          Gi.n_active = act_hi_begin - act_lo_end;
+          launch_p2g_cells<3>(P, Gi, dt, s3[cur], n_binned, bin_start, gn, status_dev, stats_dev, strict_p2g, side);
+        }
+        MPM_CUDA(cudaEventRecord(ev_side_done, side));
+        side_busy = true;
+        p2g_overlapped = true;
+      } else
       launch_g2p3(ga, P.alpha != 0.0f, mig.enabled != 0, resort3, stream);
       if (resort3) {
         if (multi)  // the new extent (dead slots dropped) = first slot of the "dead" bin of the new order
@@ -1016,9 +1074,11 @@ int mpm_handle::step_grid_g2p(float dt) {
     if (pipelined) {
       // x-slab handles run every path on the pipelined schedule: the P2G of the NEXT substep follows at once
       // (two kernels instead of the fused one), so that one exchange carries ghost sums and emigrants together
-      Phase ph(this, MPM_PHASE_P2G, n > 0 ? 1 : 0);
+      Phase ph(this, MPM_PHASE_P2G, n > 0 && !p2g_overlapped ? 1 : 0);
       const bool strict_p2g = (cfg.flags & MPM_FLAG_STRICT) != 0;
-      if (D == 2) {
+      if (p2g_overlapped) {
+        // launched above, boundary on the main stream and interior on the side stream
+      } else if (D == 2) {
         GridPtrs<2> gn = gp<2>();
         gn.g = grid_next;
         if (binned) launch_p2g_cells<2>(P, G, dt, s2[cur], n_binned, bin_start, gn, status_dev, stats_dev, strict_p2g, stream);

@@ -178,11 +178,14 @@ def test_run_continues_unsettled_and_changes_dt(oracle, flags):
     assert abs(b0["ke"] - b1["ke"]) <= 1e-3 * b0["ke"]
 
 
-def test_overlapped_schedule_3d(oracle):
-    """MPM_FLAG_OVERLAP with the fused 3D substep kernel: two slabs of 8 bin columns each (64^3 grid), interior chunks
-    on the side stream; one warm substep against the oracle, then 40 substeps with re-sorts against the plain schedule."""
+@pytest.mark.parametrize("fuse", [False, True])
+def test_overlapped_schedule_3d(oracle, fuse):
+    """MPM_FLAG_OVERLAP in 3D, two slabs of 8 bin columns each (64^3 grid): the default two-kernel path (boundary G2P + P2G
+    on the main stream, the interior's on the side stream) and the fused kernel (MPM_FLAG_FUSE_3D: its work list is
+    split); one warm substep against the oracle, then 40 substeps with re-sorts against the plain schedule."""
     from mpm_flip98a_b200.engine import FLAG_OVERLAP
-    FLAG_OVERLAP |= FLAG_FUSE_3D  # the overlapped schedule splits the fused kernel's work list
+    if fuse:
+        FLAG_OVERLAP |= FLAG_FUSE_3D
     n = 64
     dt, vol = scenes.scaled_constants(n, 3)
     p = scenes.collapse_3d(n, per_side=2, y_top=0.4, xz=(0.1, 0.9))
