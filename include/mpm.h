@@ -58,9 +58,10 @@ enum {
                                          x-slabs alike: G2P of a substep and P2G of the next run as ONE
                                          kernel, one particle read + one write per substep; 3D runs two kernels
                                          unless MPM_FLAG_FUSE_3D) */
-  MPM_FLAG_OVERLAP = 1 << 5,          /* x-slab handles on the fused schedule: bins >= 2 bin columns away from the
-                                         slab cuts run on a side stream while the boundary bins finish first, so
-                                         the caller's migration / halo exchange overlaps the interior compute */
+  MPM_FLAG_OVERLAP = 1 << 5,          /* x-slab handles (2D substep kernel; 3D two-kernel and fused schedules): bins >= 2
+                                         bin columns away from the slab cuts run on a side stream while the boundary
+                                         bins finish first, so the caller's migration / halo exchange overlaps the
+                                         interior compute; guarded per substep (MPM_E_CFL) */
   MPM_FLAG_DETERMINISTIC = 1 << 6,    /* fixed summation order: the storage is stably sorted by cell before every substep
                                          and P2G runs one thread per grid node, adding the contributions of its 3^d
                                          cells' particles sequentially in storage order -- the order the reference's
