@@ -175,10 +175,11 @@ struct mpm_handle {
     mpm_handle *h;
     Span sp;
     cudaStream_t st;
-    Phase(mpm_handle *h_, int phase, int launches, cudaStream_t on = nullptr) : h(h_), st(on ? on : h_->stream) {
+    Phase(mpm_handle *h_, int phase, int launches, cudaStream_t on = nullptr, bool enabled = true)
+        : h(h_), st(on ? on : h_->stream) {
       sp.phase = phase;
       sp.a = sp.b = nullptr;
-      if (!h->prof_on) return;
+      if (!h->prof_on || !enabled) return;
       h->prof.launches[phase] += launches;
       sp.a = h->get_event();
       sp.b = h->get_event();
@@ -975,8 +976,16 @@ int mpm_handle::step_grid_g2p(float dt) {
       fused_resort_now = false;
       if (rc) return rc;
     }
+#ifndef MPM_G2P3_TILE
+#define MPM_G2P3_TILE 0  // measured on c5 (B200): tile variant 1.83-2.23 ms at 5-7 CTAs/SM vs 1.48 ms thread-per-particle
+#endif
+    // Overlapped two-kernel schedule (MPM_FLAG_OVERLAP, no re-sort in this substep): see below.  Its launches are timed
+    // by their own spans (boundary under MPM_PHASE_MIGRATE, interior under MPM_PHASE_G2P on the side stream), so the
+    // enclosing G2P span stays off -- it would count the boundary work a second time.
+    const bool ov3 = fast3 && !MPM_G2P3_TILE && overlap && !resort3 && n > 0 && act_hi_begin > act_lo_end &&
+                     slot_hi_begin > slot_lo_end;
     if (fast3) {
-      Phase ph(this, MPM_PHASE_G2P, n > 0 ? 1 : 0);
+      Phase ph(this, MPM_PHASE_G2P, n > 0 && !ov3 ? 1 : 0, nullptr, !ov3);
       G2p3Args ga;
       ga.P = P;
       ga.dt = dt;
@@ -995,9 +1004,6 @@ int mpm_handle::step_grid_g2p(float dt) {
       ga.dev_n = dev_ext;
       ga.chunks = chunks_buf[bs];
       ga.n_chunks = n_chunks;
-#ifndef MPM_G2P3_TILE
-#define MPM_G2P3_TILE 0  // measured on c5 (B200): tile variant 1.83-2.23 ms at 5-7 CTAs/SM vs 1.48 ms thread-per-particle
-#endif
       if (MPM_G2P3_TILE && chunk_offs) {
         // binned range: CTA per chunk with the node tile in shared memory; immigrant tail: thread per particle
         launch_g2p3_tile(ga, P.alpha != 0.0f, mig.enabled != 0, resort3, stream);
@@ -1008,7 +1014,6 @@ int mpm_handle::step_grid_g2p(float dt) {
       // the main stream -- their emigrants and shared node planes are what the caller exchanges next -- while G2P + P2G of
       // the interior follow on the low-priority side stream.  An interior particle can neither emigrate nor touch a
       // shared plane: checked per particle by the kernel (mig.interior), flagged as MPM_E_CFL.
-      const bool ov3 = overlap && !resort3 && n > 0 && act_hi_begin > act_lo_end && slot_hi_begin > slot_lo_end;
       if (ov3) {
         const bool flip3 = P.alpha != 0.0f;
         const bool strict_p2g = false;  // fast3d() excludes MPM_FLAG_STRICT

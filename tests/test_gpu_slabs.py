@@ -209,6 +209,33 @@ def test_overlapped_schedule_3d(oracle, fuse):
     assert rel_l2(a[:, 0:3], b[:, 0:3]) <= 1e-5 and rel_l2(a[:, 3:6], b[:, 3:6]) <= 1e-3
 
 
+def test_overlapped_schedule_3d_times_each_launch_once():
+    """Per-phase accounting of the overlapped two-kernel 3D schedule (mpm_profile, what bench.py's roofline reads): per
+    substep the interior's G2P + P2G are the two launches under "g2p" (side stream), the boundary's five launches and the
+    immigrant unpack sit under "migrate", and no enclosing span counts the boundary work a second time."""
+    from mpm_flip98a_b200.engine import FLAG_OVERLAP
+    n = 64
+    dt, vol = scenes.scaled_constants(n, 3)
+    p = scenes.collapse_3d(n, per_side=2, y_top=0.4, xz=(0.1, 0.9))
+    ranks, ex, slabs = parallel.make_local_cluster(mpm.Engine, p, 3, n, 2, dt=dt, vol_p=vol, flags=FLAG_OVERLAP,
+                                                   rebin_every=64, shared_stream=True)
+    parallel.step_local(ranks, ex, 3, settle=False)
+    for r in ranks:
+        r.e.profile_enable(True)
+    parallel.step_local(ranks, ex, 6, settle=False)
+    profs = [r.e.profile() for r in ranks]
+    status = [r.e.poll_status() for r in ranks]
+    for r in ranks:
+        r.e.close()
+    assert status == [0, 0]
+    for pr in profs:
+        assert pr["substeps"] == 6
+        assert pr["g2p"][1] == 2 * 6, pr      # interior G2P + interior P2G, nothing else
+        assert pr["p2g"][1] == 0, pr          # the next P2G was launched by the overlapped schedule
+        assert pr["migrate"][1] == (5 + 3) * 6, pr
+        assert pr["g2p"][0] > 0 and pr["migrate"][0] > 0
+
+
 def test_overlap_guard_flags_a_too_long_resort_interval():
     """The interior launch of the overlapped schedule skips the migration code; what licenses that -- no particle can
     have travelled from an interior bin to the slab cut since the last re-sort -- is checked on the device every substep
