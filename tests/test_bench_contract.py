@@ -69,3 +69,53 @@ def test_rebalanced_cuts_equalise_measured_cost():
     s3 = parallel.partition_filled(324, 2, 4)
     n3 = bench.rebalanced_cuts(s3, [3.6, 4.75], 324, 4, (0.05, 0.95))
     assert n3[0][1] > s3[0][1] and n3[0][1] % 4 == 0
+
+
+def _fake_profile(substeps, g2p, p2g, migrate, fused):
+    ph = {"clear": (0.0, 0), "p2g": p2g, "grid": (0.3 * substeps, substeps), "g2p": g2p, "bin": (1.9, 6),
+          "halo": (0.01 * substeps, 2 * substeps), "migrate": migrate}
+    ph.update(substeps=substeps, fallback_particles=0, rebin_interval=24, fused_substeps=substeps if fused else 0)
+    return ph
+
+
+def test_roofline_of_the_json_line_is_recomputable():
+    """bench.make_line: `roofline.achieved` = algorithmic bytes per particle-substep x this rank's particles / the dominant
+    kernel's mean time.  Single GPU: the fused kernel's span; overlapped x-slab runs (2D and 3D): the interior span PLUS
+    the boundary launches of the same kernels, which the engine times under "migrate"."""
+    sys.path.insert(0, ROOT)
+    import argparse
+    import bench
+    K, n = 20, 244558728
+    args = argparse.Namespace(steps=K, warmup=5, workload="c4", naive=False, warm_substeps=2000)
+    clocks = {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": [], "samples": 6}
+    # single GPU, fused 2D kernel
+    prof = _fake_profile(K, g2p=(5.9 * K, K), p2g=(0.0, 0), migrate=(0.0, 0), fused=True)
+    d = bench.make_line(args, 1, n, n, 14, 2, 8192, 0.0, 1e-6, "c4", 6.3 * K, n / 6.3e-3, 4e9, prof, clocks,
+                        scaling="weak", extra_config={})
+    r = d["roofline"]
+    assert r["kernel"] == "g2p2g" and r["algorithmic_bytes_per_particle"] == 140
+    assert abs(r["kernel_ms"] - 5.9) < 1e-9 and abs(r["achieved"] - 140 * n / 5.9e-3 / 1e9) < 1e-6 * r["achieved"]
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and d["gpu_launches"] == K + K + 6 + 2 * K
+    assert d["ms_per_step"] == pytest.approx(6.3) and d["config"]["name"] == "c4" and d["parity"]
+    json.dumps(d)
+    # 2 GPUs, overlapped 2D schedule: boundary bins under "migrate"
+    prof = _fake_profile(K, g2p=(5.8 * K, K), p2g=(0.0, 0), migrate=(0.1 * K, 5 * K), fused=True)
+    d = bench.make_line(args, 2, 2 * n, n, 14, 2, 11584, 0.0, 1e-6, "c4", 6.4 * K, 2 * n / 6.4e-3, 7e9, prof, clocks,
+                        scaling="weak", extra_config={"overlap": True, "overlap_3d": False})
+    assert d["roofline"]["kernel"] == "g2p2g" and d["roofline"]["kernel_ms"] == pytest.approx(5.9)
+    assert d["config"]["overlap"] is True and d["n_gpus"] == 2
+    # 2 GPUs, overlapped two-kernel 3D schedule: interior G2P + P2G on the side stream are one "g2p" span
+    args5 = argparse.Namespace(steps=K, warmup=5, workload="c5", naive=False, warm_substeps=400)
+    n5 = 32163200
+    prof = _fake_profile(K, g2p=(3.0 * K, 2 * K), p2g=(0.0, 0), migrate=(0.3 * K, 8 * K), fused=False)
+    d = bench.make_line(args5, 2, 2 * n5, n5, 26, 3, 324, 0.0, 3e-5, "c5", 3.6 * K, 2 * n5 / 3.6e-3, 3e9, prof, clocks,
+                        scaling="weak", extra_config={"overlap": True, "overlap_3d": True})
+    r = d["roofline"]
+    assert r["kernel"] == "g2p+p2g" and r["algorithmic_bytes_per_particle"] == 260 and r["kernel_ms"] == pytest.approx(3.3)
+    # single GPU 3D: two kernels, the slower one is reported with its own share of the bytes
+    prof = _fake_profile(K, g2p=(1.48 * K, K), p2g=(1.73 * K, K), migrate=(0.0, 0), fused=False)
+    d = bench.make_line(args5, 1, n5, n5, 26, 3, 256, 0.0, 3e-5, "c5", 3.35 * K, n5 / 3.35e-3, 2e9, prof, clocks,
+                        scaling="weak", extra_config={})
+    r = d["roofline"]
+    assert r["kernel"] == "p2g" and r["algorithmic_bytes_per_particle"] == 104 and r["kernel_ms"] == pytest.approx(1.73)
+    assert r["whole_substep"]["algorithmic_bytes_per_particle"] == 260
