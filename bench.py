@@ -15,6 +15,9 @@ cpp_validation/mls-mpm88-explained.cpp:49-180) over every particle of the worklo
              scene: on all host threads (the threaded oracle is bitwise its serial self) and, beside it, on one
              thread -- the reference is single-threaded as shipped
 `--impl reference` times that CPU path alone and prints the same line with "impl": "reference".
+`config` holds only what NAMES the workload (workload, name, dim, n_grid, particles, alpha, dt, l2) and is the same object
+in both arms of one command line; what is specific to an arm sits beside it: `engine` (kernel path, warm-up, and for
+N > 1 the slab decomposition, calibration, exchange and per-rank phases) / `sample` (the CPU arm's bounded sample).
 The timed state is a MOVING scene: c4 starts as a cellular flow (scenes.swirl_velocity, peak speed 3 = 0.024 cells
 per substep, the range of the reference's own scene) and every workload is warmed on the GPU (2000 substeps for
 c4) before anything is timed; the storage re-sorts that fall due run inside the timed steps (their interval is
@@ -82,6 +85,55 @@ def build_scene(name, n_grid=None):
         p = scenes.collapse_3d(n, per_side=2)
     dt, vol = scenes.scaled_constants(n, dim)
     return p, dim, n, alpha, dt, vol
+
+
+def scaled_n_grid(name, world, scaling):
+    """Grid size of a run on `world` GPUs.  weak scaling: particles AND grid nodes per GPU stay what one GPU has at N = 1
+    (2D: n_grid = n0*sqrt(N); 3D: n_grid = n0*cbrt(N)), the domain stays the unit box; strong scaling: the N = 1 problem."""
+    _, dim, n0, _ = WORKLOADS[name]
+    if world == 1 or scaling != "weak":
+        return n0
+    edge = 8 if dim == 2 else 4
+    f = world ** (0.5 if dim == 2 else 1.0 / 3.0)
+    align = edge * world if dim == 2 else edge
+    return int(round(n0 * f / align)) * align
+
+
+def workload_particles(name, n_grid):
+    """Particles of workload `name` at grid size n_grid, without generating them (the scenes are cell-aligned jittered
+    lattices: cells of the filled boxes x particles per cell; checked against the generators in tests/)."""
+    from mpm_flip98a_b200 import scenes
+    if name == "c1":
+        return 3000
+    if name == "c2":
+        return sum(scenes.box_count((cx - 0.14, cy - 0.14), (cx + 0.14, cy + 0.14), n_grid, 4)
+                   for cx, cy in ((0.55, 0.20), (0.45, 0.49), (0.55, 0.78)))
+    if name == "c3":
+        return scenes.box_count((0.05, 0.05), (0.05 + 0.47, 0.05 + 0.90), n_grid, 3)
+    if name == "c4":
+        return scenes.slab_fill_2d_count(n_grid)
+    return scenes.box_count((0.05, 0.05, 0.05), (0.95, 0.35, 0.95), n_grid, 2)
+
+
+def config_dict(name, n_grid, particles, dt, world):
+    """`config` of the JSON line: the keys that NAME the workload, identical in both arms (ours / --impl reference) of the
+    same command line.  What is specific to an arm (kernel path, slab decomposition, the CPU arm's bounded sample) sits
+    in its own top-level object."""
+    descr, dim, _, alpha = WORKLOADS[name]
+    per_gpu = particles / float(world) * (14 if dim == 2 else 26) * 4
+    return {"workload": descr, "name": name, "dim": dim, "n_grid": int(n_grid), "particles": int(particles),
+            "alpha": alpha, "dt": float(dt),
+            "l2": "state (%.1f GB per GPU) larger than L2; no flush" % (per_gpu / 1e9)
+            if per_gpu > 2.5e8 else "state fits L2 (small workload)"}
+
+
+def workload_config(name, world=1, scaling="weak"):
+    """config_dict of a command line, computed without touching a GPU (the reference arm uses this)."""
+    from mpm_flip98a_b200 import scenes
+    dim = WORKLOADS[name][1]
+    n_grid = scaled_n_grid(name, world, scaling)
+    dt = 1e-4 if name == "c1" else scenes.scaled_constants(n_grid, dim)[0]  # c1: the shipped constant (:11)
+    return config_dict(name, n_grid, workload_particles(name, n_grid), dt, world)
 
 
 class ClockSampler(threading.Thread):
@@ -209,14 +261,14 @@ def run_reference(args):
         O.advance(P, dt, p, 1, threads=T)
     el = time.perf_counter() - t0
     value = len(p) * args.steps / el
-    descr, dim, n_grid, alpha = WORKLOADS[args.workload]
     sample = "one substep over a bounded sample per step: %s scene at n_grid=%d, %d particles" % (
         args.workload, P.n_grid, len(p))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "particle-substeps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": descr, "dim": dim, "n_grid": n_grid, "alpha": alpha, "sample": sample},
+            "config": workload_config(args.workload, args.gpus, args.scaling),  # == the GPU arm's of this command line
+            "sample": sample,
             "cpu_baseline": {"value": value, "unit": "particle-substeps/s", "cores": T, "kind": "port",
                              "sample": sample, "single_thread_value": val1, "single_thread_sample": desc1},
             "e2e": {"value": value, "unit": "particle-substeps/s", "h2d_bytes_per_step": 0,
@@ -462,13 +514,11 @@ def make_line(args, world, n_total, n_local, words, dim, n_grid, alpha, dt, desc
                 "phase_ms_per_substep": {k: v[0] / max(1, prof["substeps"]) for k, v in phases.items()}}
     launches = int(sum(v[1] for v in phases.values()))
 
-    cfg = {"workload": descr, "name": args.workload, "dim": dim, "n_grid": n_grid, "particles": n_total,
-           "alpha": alpha, "dt": dt, "path": "naive" if args.naive else ("binned, fused G2P->P2G" if prof.get("fused_substeps", 0) else "binned"),
-           "warm_substeps": args.warm_substeps,
-           "l2": "state (%.1f GB per GPU) larger than L2; no flush" % (n_local * words * 4 / 1e9)
-           if n_local * words * 4 > 2.5e8 else "state fits L2 (small workload)"}
-    cfg.update(extra_config)
-    return {"metric": METRIC, "value": value, "unit": "particle-substeps/s", "n_gpus": world,
+    cfg = config_dict(args.workload, n_grid, n_total, dt, world)
+    engine = {"path": "naive" if args.naive else ("binned, fused G2P->P2G" if prof.get("fused_substeps", 0) else "binned"),
+              "warm_substeps": args.warm_substeps}
+    engine.update(extra_config)  # N > 1: the slab decomposition, calibration, exchange, per-rank phases
+    return {"metric": METRIC, "engine": engine, "value": value, "unit": "particle-substeps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": cfg,
@@ -504,12 +554,7 @@ def slab_plan(args, world):
     name = args.workload
     descr, dim, n0, alpha = WORKLOADS[name]
     edge = 8 if dim == 2 else 4
-    if args.scaling == "weak":
-        f = world ** (0.5 if dim == 2 else 1.0 / 3.0)
-        align = edge * world if dim == 2 else edge
-        n_grid = int(round(n0 * f / align)) * align
-    else:
-        n_grid = n0
+    n_grid = scaled_n_grid(name, world, args.scaling)
     x_range = (0.05, 0.95) if name in ("c4", "c5") else (0.05, 0.52)
     slabs = parallel.partition_filled(n_grid, world, edge, x_range=x_range)  # equal particle counts
 

@@ -48,6 +48,14 @@ def _jittered_box(lo, hi, n_grid, per_side, rng, dim):
     return ((sub + jit) * (dx / per_side)).astype(np.float32)
 
 
+def box_count(lo, hi, n_grid, per_side):
+    """Number of particles _jittered_box generates for the box [lo, hi): its cells x per_side^dim."""
+    n = 1
+    for l, h in zip(lo, hi):
+        n *= max(0, int(np.floor(h * n_grid + 1e-9)) - int(np.ceil(l * n_grid - 1e-9))) * per_side
+    return n
+
+
 def three_blocks_2d(n_grid=512, per_side=4, seed=1, side=0.28):
     """BASELINE config 2: three squares (fluid / jelly / snow), per_side^2 particles per cell."""
     rng = np.random.RandomState(seed)

@@ -17,7 +17,7 @@ for f in sorted(glob.glob(os.path.join(here, tag + "_bench_*.json"))):
     ws = r["whole_substep"]
     note = "kernel %s %.3f ms (%.0f %% of measured HBM)" % (r["kernel"], r["kernel_ms"], 100 * r["frac"])
     if d["n_gpus"] > 1:
-        note += "; bubble %.2f ms; %s" % (c.get("exchange_bubble_ms_per_step", 0), d["scaling"])
+        note += "; bubble %.2f ms; %s" % (d.get("engine", c).get("exchange_bubble_ms_per_step", 0), d["scaling"])
     rows.append((os.path.basename(f), "%s, %.1f M particles, n_grid %d" % (c["name"], c["particles"] / 1e6, c["n_grid"]), d["n_gpus"],
                  "%.2f G" % (d["value"] / 1e9), "%.3f" % d["ms_per_step"], "%.0f" % ws["achieved"], "%.1f %%" % (100 * ws["frac"]),
                  "%.1f %%" % (100 * ws["frac_of_nominal_8TBs"]), note + "; e2e %.2f G" % (d["e2e"]["value"] / 1e9)))

@@ -23,6 +23,12 @@ def test_reference_arm_prints_one_json_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    # `config` names the workload of the command line -- the same object the GPU arm prints -- and the bounded sample the
+    # CPU arm actually ran is described beside it
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config("c2") and d["config"]["particles"] == 979264
+    assert "n_grid=512" in d["sample"] and d["sample"] == cb["sample"]
     assert cb["single_thread_value"] > 1e5  # the reference as shipped has no threads: reported beside the threaded rate
 
 
@@ -103,7 +109,7 @@ def test_roofline_of_the_json_line_is_recomputable():
     d = bench.make_line(args, 2, 2 * n, n, 14, 2, 11584, 0.0, 1e-6, "c4", 6.4 * K, 2 * n / 6.4e-3, 7e9, prof, clocks,
                         scaling="weak", extra_config={"overlap": True, "overlap_3d": False})
     assert d["roofline"]["kernel"] == "g2p2g" and d["roofline"]["kernel_ms"] == pytest.approx(5.9)
-    assert d["config"]["overlap"] is True and d["n_gpus"] == 2
+    assert d["engine"]["overlap"] is True and d["n_gpus"] == 2 and "overlap" not in d["config"]
     # 2 GPUs, overlapped two-kernel 3D schedule: interior G2P + P2G on the side stream are one "g2p" span
     args5 = argparse.Namespace(steps=K, warmup=5, workload="c5", naive=False, warm_substeps=400)
     n5 = 32163200
@@ -119,3 +125,30 @@ def test_roofline_of_the_json_line_is_recomputable():
     r = d["roofline"]
     assert r["kernel"] == "p2g" and r["algorithmic_bytes_per_particle"] == 104 and r["kernel_ms"] == pytest.approx(1.73)
     assert r["whole_substep"]["algorithmic_bytes_per_particle"] == 260
+
+
+def test_both_arms_print_the_same_config():
+    """bench.workload_config (what `--impl reference` prints as `config`) against the committed GPU-arm lines of this round
+    (profiles/r02_bench_*.json: N = 1, 2, 8; weak and strong; 2D and 3D) and against the scene generators at small sizes."""
+    sys.path.insert(0, ROOT)
+    import glob
+    import bench
+    from mpm_flip98a_b200 import scenes
+    seen = 0
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r02_bench_c*.json"))):
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        c = d["config"]
+        w = bench.workload_config(c["name"], d["n_gpus"], d["scaling"])
+        for k in ("workload", "name", "dim", "n_grid", "particles", "alpha", "dt"):
+            assert w[k] == c[k], (os.path.basename(f), k, w[k], c[k])
+        seen += 1
+    assert seen >= 9
+    assert bench.workload_particles("c2", 256) == len(scenes.three_blocks_2d(256, per_side=4))
+    assert bench.workload_particles("c3", 320) == len(scenes.dam_break_2d(320, per_side=3, width=0.47))
+    assert bench.workload_particles("c4", 328) == len(scenes.slab_fill_2d(328, per_side=3))
+    assert bench.workload_particles("c5", 44) == len(scenes.collapse_3d(44, per_side=2))
+    assert bench.workload_particles("c5", 44) == len(scenes.collapse_3d(44, per_side=2, columns=(0, 20))) + \
+        len(scenes.collapse_3d(44, per_side=2, columns=(20, 44)))
+    # the GPU arm's make_line and the CPU arm's workload_config go through the same config_dict
+    assert bench.workload_config("c4", 8)["l2"].startswith("state (13.7 GB per GPU)")
+    assert bench.workload_config("c1") == bench.config_dict("c1", 80, 3000, 1e-4, 1)
