@@ -518,10 +518,10 @@ def make_line(args, world, n_total, n_local, words, dim, n_grid, alpha, dt, desc
     engine = {"path": "naive" if args.naive else ("binned, fused G2P->P2G" if prof.get("fused_substeps", 0) else "binned"),
               "warm_substeps": args.warm_substeps}
     engine.update(extra_config)  # N > 1: the slab decomposition, calibration, exchange, per-rank phases
-    return {"metric": METRIC, "engine": engine, "value": value, "unit": "particle-substeps/s", "n_gpus": world,
+    return {"metric": METRIC, "value": value, "unit": "particle-substeps/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": cfg,
+            "data": "synthetic", "config": cfg, "engine": engine,
             "e2e": {"value": e2e_value, "unit": "particle-substeps/s", "h2d_bytes_per_step": n_total * words * 4,
                     "d2h_bytes_per_step": n_total * words * 4, "substeps_per_step": FRAME,
                     "call": "mpm_upload_particles + %d substeps + mpm_read_particles, pinned host buffers" % FRAME},

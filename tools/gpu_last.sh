@@ -1,6 +1,5 @@
 #!/bin/bash
-# last GPU seconds of round 2 (1 GPU, < 1 min): smoke() and the 2D overlapped-schedule tests on the final libmpm.so
+# last GPU seconds of round 2 (1 GPU, ~20 s): the GPU arm of bench.py end to end on the smallest workload after the
+# `config` / `engine` split of the JSON line
 mkdir -p gpurun_out
-timeout 18 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r02_smoke_last.log 2>&1; echo "smoke rc=$?" > gpurun_out/r2v_box.txt
-timeout 35 python -m pytest tests/test_gpu_slabs.py -m gpu -q -x -k "overlapped_schedule_wide" > gpurun_out/r02_pytest_overlap2d_last.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2v_box.txt
-cat gpurun_out/r2v_box.txt
+timeout 30 python bench.py --workload c1 --steps 20 --warmup 5 --no-cpu --e2e-calls 1 > gpurun_out/r02_bench_c1_last.json 2> gpurun_out/r02_bench_c1_last.err; echo "bench c1 rc=$?"
